@@ -1,0 +1,1019 @@
+// lz4b200_api.cu — host runtime and C ABI (include/lz4b200.h) of the B200 LZ4 block codec.
+//
+// Everything here is product code: contexts, launch plumbing, host<->device staging and the
+// frame container (header / BlockInfo / checksums), which is host-side bookkeeping around the
+// two block kernels.  There is no CPU codec in this library: without a CUDA device every entry
+// point that has work to do fails with LZ4B200_CUDA_ERROR.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lz4b200_kernels.cuh"
+
+using namespace lz4b200;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers used by the frame path
+// ---------------------------------------------------------------------------------------------
+namespace lz4b200 {
+
+// Exclusive scan of sizes[0..n) into offs[0..n], offs[n] = total.  One CTA; n is a block count
+// (<= a few 100k), so a single-CTA chunked scan is far below launch noise.
+__global__ void __launch_bounds__(1024) scan_sizes_kernel(const uint32_t *sizes, uint64_t *offs, uint32_t n)
+{
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < n ? sizes[i] : 0, x = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(kFull, x, d);
+            if ((threadIdx.x & 31) >= d) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t w = warp_sums[threadIdx.x], s = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t y = __shfl_up_sync(kFull, s, d);
+                if (threadIdx.x >= d) s += y;
+            }
+            warp_sums[threadIdx.x] = s - w;
+        }
+        __syncthreads();
+        uint64_t excl = carry + warp_sums[threadIdx.x >> 5] + x - v;
+        if (i < n) offs[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[n] = carry;
+}
+
+// Generic gather: segment b copies len[b] bytes from src_base[sel] + src_off[b] to dst + dst_off[b],
+// optionally preceded by a 4-byte little-endian word (the frame BlockInfo).  One CTA per segment
+// slice; byte-granular head/tail, 16-byte body when co-aligned.
+struct GatherArgs {
+    const uint8_t *src_a;          // segment source when pick[b] == 0
+    const uint8_t *src_b;          // segment source when pick[b] != 0
+    const uint64_t *off_a;
+    const uint64_t *off_b;
+    const uint32_t *len_a;
+    const uint32_t *len_b;
+    const uint8_t *pick;           // may be null (always a)
+    const uint32_t *prefix_word;   // may be null; else written as 4 LE bytes before the payload
+    uint8_t *dst;
+    const uint64_t *dst_off;
+    uint32_t nseg;
+};
+
+__global__ void __launch_bounds__(256) gather_segments_kernel(GatherArgs g)
+{
+    for (uint32_t b = blockIdx.x; b < g.nseg; b += gridDim.x) {
+        const bool second = g.pick && g.pick[b];
+        const uint8_t *s = second ? g.src_b + g.off_b[b] : g.src_a + g.off_a[b];
+        const uint32_t len = second ? g.len_b[b] : g.len_a[b];
+        uint8_t *d = g.dst + g.dst_off[b];
+        if (g.prefix_word) {
+            if (threadIdx.x < 4) d[threadIdx.x] = (uint8_t)(g.prefix_word[b] >> (8 * threadIdx.x));
+            d += 4;
+        }
+        const uint32_t dm = (uint32_t)(reinterpret_cast<uintptr_t>(d) & 15u);
+        const uint32_t sm = (uint32_t)(reinterpret_cast<uintptr_t>(s) & 15u);
+        if (dm == sm && len >= 64) {
+            uint32_t head = (16u - dm) & 15u;
+            if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+            uint32_t body = (len - head) >> 4;
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s + head);
+            uint4 *d4 = reinterpret_cast<uint4 *>(d + head);
+            for (uint32_t i = threadIdx.x; i < body; i += blockDim.x) d4[i] = s4[i];
+            uint32_t done = head + (body << 4);
+            if (done + threadIdx.x < len) d[done + threadIdx.x] = s[done + threadIdx.x];
+        } else {
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) d[i] = s[i];
+        }
+    }
+}
+
+// Frame encoder bookkeeping for a block range: per block, decide compressed-vs-stored
+// (frame/compress.rs:301-306) and produce BlockInfo word + segment size.
+__global__ void frame_block_info_kernel(const uint32_t *comp_len, const uint32_t *raw_len, uint32_t n,
+                                        uint32_t *info_word, uint8_t *pick_raw, uint32_t *seg_size,
+                                        uint32_t *payload_len)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = comp_len[i], r = raw_len[i];
+    bool stored = !(c < r);
+    info_word[i] = stored ? (r | 0x80000000u) : c;
+    pick_raw[i] = stored ? 1 : 0;
+    payload_len[i] = stored ? r : c;
+    seg_size[i] = 4u + (stored ? r : c);
+}
+
+// Descriptor generator for a run of equal-sized blocks cut from one contiguous buffer.
+__global__ void make_uniform_desc_kernel(uint64_t total_len, uint32_t block, uint64_t out_stride,
+                                         uint64_t first_block, uint64_t fresh_period, uint32_t n,
+                                         uint64_t *in_off, uint32_t *in_len, uint64_t *out_off,
+                                         uint32_t *out_cap, uint8_t *flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t o = (uint64_t)i * block;
+    uint64_t rem = total_len - o;
+    in_off[i] = o;
+    in_len[i] = (uint32_t)(rem < block ? rem : block);
+    out_off[i] = (uint64_t)i * out_stride;
+    out_cap[i] = (uint32_t)out_stride;
+    if (flags) {
+        uint64_t k = first_block + i;
+        bool fresh = (k % fresh_period) == 0;
+        flags[i] = (uint8_t)(LZ4B200_BLOCK_HASH5_ALWAYS | (fresh ? 0u : LZ4B200_BLOCK_CONT));
+    }
+}
+
+}  // namespace lz4b200
+
+// ---------------------------------------------------------------------------------------------
+// XXH32 (host) — header checksum byte, block and content checksums
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline void wr32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
+inline uint32_t rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+constexpr uint32_t kP1 = 2654435761u, kP2 = 2246822519u, kP3 = 3266489917u, kP4 = 668265263u, kP5 = 374761393u;
+
+struct Xxh32 {
+    uint32_t acc[4];
+    uint8_t buf[16];
+    uint32_t fill = 0;
+    uint64_t total = 0;
+    uint32_t seed;
+    explicit Xxh32(uint32_t s = 0) : seed(s)
+    {
+        acc[0] = s + kP1 + kP2; acc[1] = s + kP2; acc[2] = s; acc[3] = s - kP1;
+    }
+    static uint32_t round(uint32_t a, uint32_t v) { return rotl(a + v * kP2, 13) * kP1; }
+    void stripe(const uint8_t *p)
+    {
+        for (int i = 0; i < 4; i++) acc[i] = round(acc[i], rd32(p + 4 * i));
+    }
+    void update(const uint8_t *p, size_t n)
+    {
+        total += n;
+        if (fill) {
+            size_t take = std::min<size_t>(16 - fill, n);
+            memcpy(buf + fill, p, take); fill += (uint32_t)take; p += take; n -= take;
+            if (fill < 16) return;
+            stripe(buf); fill = 0;
+        }
+        for (; n >= 16; p += 16, n -= 16) stripe(p);
+        if (n) { memcpy(buf, p, n); fill = (uint32_t)n; }
+    }
+    uint32_t digest() const
+    {
+        uint32_t h = total >= 16 ? rotl(acc[0], 1) + rotl(acc[1], 7) + rotl(acc[2], 12) + rotl(acc[3], 18)
+                                 : seed + kP5;
+        h += (uint32_t)total;
+        const uint8_t *p = buf, *e = buf + fill;
+        for (; p + 4 <= e; p += 4) h = rotl(h + rd32(p) * kP3, 17) * kP4;
+        for (; p < e; p++) h = rotl(h + (*p) * kP5, 11) * kP1;
+        h ^= h >> 15; h *= kP2; h ^= h >> 13; h *= kP3; h ^= h >> 16;
+        return h;
+    }
+};
+
+size_t block_size_bytes(int id)
+{
+    switch (id) {
+    case 4: return 64u << 10;
+    case 5: return 256u << 10;
+    case 6: return 1u << 20;
+    case 7: return 4u << 20;
+    case 8: return 8u << 20;
+    default: return 0;
+    }
+}
+
+// BlockSize::from_buf_length — frame/header.rs:57-67
+int auto_block_size_id(size_t first_write_len)
+{
+    if (first_write_len > (256u << 10)) return 7;
+    if (first_write_len > (64u << 10)) return 5;
+    return 4;
+}
+
+// Number of consecutive full blocks that share one table epoch before FrameEncoder repositions
+// its table (frame/compress.rs:266-271): block k is FRESH iff k % period == 0.
+uint64_t fresh_period(size_t bs)
+{
+    // reposition fires at the first block whose starting offset off satisfies off + bs + 65536 >= 2^31 - 1
+    uint64_t limit = 0x7FFFFFFFull - 65536ull - bs;      // off >= limit
+    return (limit + bs - 1) / bs;
+}
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct lz4b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *d_tickets = nullptr;            // 3 x {next, retired}
+    int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
+    std::string last_error;
+
+    // scratch for host-pointer and frame entry points
+    DevBuf<uint8_t> d_in, d_out, d_slots, d_flags, d_pick;
+    DevBuf<uint64_t> d_in_off, d_out_off, d_seg_off, d_expected, d_off_b;
+    DevBuf<uint32_t> d_in_len, d_out_cap, d_out_len, d_info, d_seg_size, d_payload_len;
+    DevBuf<int32_t> d_status;
+
+    bool check(cudaError_t e, const char *what)
+    {
+        if (e == cudaSuccess) return true;
+        last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        return false;
+    }
+};
+
+namespace {
+
+constexpr int kEnc16Warps = 4;     // 4 x 8 KiB tables per CTA
+constexpr int kEnc32Warps = 2;     // 2 x 16 KiB tables per CTA
+
+#define CTX_CUDA(ctx, call)                                              \
+    do {                                                                 \
+        if (!(ctx)->check((call), #call)) return LZ4B200_CUDA_ERROR;     \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s)
+{
+    if (args.nblocks == 0) return LZ4B200_OK;
+    BatchArgs a = args;
+    a.tickets = ctx->d_tickets;
+    uint32_t want = (a.nblocks + kDecWarpsPerCta - 1) / kDecWarpsPerCta;
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->dec_ctas_per_sm));
+    lz4_decompress_blocks<<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    CTX_CUDA(ctx, cudaGetLastError());
+    return LZ4B200_OK;
+}
+
+lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s)
+{
+    if (args.nblocks == 0) return LZ4B200_OK;
+    BatchArgs a = args;
+    // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
+    {
+        uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
+        uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16_ctas_per_sm));
+        lz4_compress_blocks<uint16_t, kEnc16Warps>
+            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, ctx->d_tickets + 2);
+        CTX_CUDA(ctx, cudaGetLastError());
+    }
+    if (max_in_len == 0 || max_in_len > 65536u) {
+        uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
+        uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
+        lz4_compress_blocks<uint32_t, kEnc32Warps>
+            <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, ctx->d_tickets + 4);
+        CTX_CUDA(ctx, cudaGetLastError());
+    }
+    return LZ4B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lz4b200_abi_version(void) { return LZ4B200_ABI_VERSION; }
+
+const char *lz4b200_status_string(int s)
+{
+    switch (s) {
+    case LZ4B200_OK: return "ok";
+    case LZ4B200_COMPRESS_OUTPUT_TOO_SMALL:
+        return "output is too small for the compressed data, use get_maximum_output_size to reserve enough space";
+    case LZ4B200_DEC_OUTPUT_TOO_SMALL: return "provided output is too small for the decompressed data";
+    case LZ4B200_DEC_LITERAL_OUT_OF_BOUNDS: return "literal is out of bounds of the input";
+    case LZ4B200_DEC_EXPECTED_ANOTHER_BYTE: return "expected another byte, found none";
+    case LZ4B200_DEC_OFFSET_ZERO: return "0 is not a valid match offset";
+    case LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS: return "the offset to copy is not contained in the decompressed buffer";
+    case LZ4B200_FRAME_DECOMPRESSION_ERROR: return "frame: block decompression error";
+    case LZ4B200_FRAME_WRONG_MAGIC: return "frame: wrong magic number";
+    case LZ4B200_FRAME_RESERVED_BITS: return "frame: reserved bits set";
+    case LZ4B200_FRAME_UNSUPPORTED_VERSION: return "frame: unsupported version";
+    case LZ4B200_FRAME_UNSUPPORTED_BLOCKSIZE: return "frame: unsupported block size";
+    case LZ4B200_FRAME_HEADER_CHECKSUM: return "frame: header checksum error";
+    case LZ4B200_FRAME_BLOCK_CHECKSUM: return "frame: block checksum error";
+    case LZ4B200_FRAME_CONTENT_CHECKSUM: return "frame: content checksum error";
+    case LZ4B200_FRAME_CONTENT_LENGTH: return "frame: content length differs from the header";
+    case LZ4B200_FRAME_BLOCK_TOO_BIG: return "frame: block too big";
+    case LZ4B200_FRAME_SKIPPABLE: return "frame: skippable frame";
+    case LZ4B200_FRAME_DICTIONARY: return "frame: dictionaries are not supported";
+    case LZ4B200_FRAME_IO_EOF: return "frame: unexpected end of input";
+    case LZ4B200_FRAME_LINKED_UNSUPPORTED: return "frame: linked blocks are not supported on the GPU path";
+    case LZ4B200_FRAME_OUTPUT_FULL: return "frame: output buffer exhausted";
+    case LZ4B200_INVALID_ARGUMENT: return "invalid argument";
+    case LZ4B200_CUDA_ERROR: return "CUDA error";
+    default: return "unknown status";
+    }
+}
+
+const char *lz4b200_last_cuda_error(const lz4b200_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
+{
+    if (!out) return LZ4B200_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LZ4B200_CUDA_ERROR;
+    lz4b200_ctx *ctx = new lz4b200_ctx();
+    ctx->device = device;
+    DeviceGuard guard(device);
+    bool ok = ctx->check(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count") &&
+              ctx->check(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "stream") &&
+              ctx->check(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tickets), 8 * sizeof(uint32_t)), "tickets") &&
+              ctx->check(cudaMemset(ctx->d_tickets, 0, 8 * sizeof(uint32_t)), "tickets memset");
+    if (ok) {
+        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks,
+                                                                      kDecWarpsPerCta * 32, 0), "occupancy dec") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
+                            kEnc16Warps * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
+                            kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32");
+    }
+    if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
+        fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
+        lz4b200_ctx_destroy(ctx);
+        return LZ4B200_CUDA_ERROR;
+    }
+    *out = ctx;
+    return LZ4B200_OK;
+}
+
+void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    ctx->d_in.release(); ctx->d_out.release(); ctx->d_slots.release(); ctx->d_flags.release(); ctx->d_pick.release();
+    ctx->d_in_off.release(); ctx->d_out_off.release(); ctx->d_seg_off.release(); ctx->d_expected.release();
+    ctx->d_off_b.release();
+    ctx->d_in_len.release(); ctx->d_out_cap.release(); ctx->d_out_len.release(); ctx->d_info.release();
+    ctx->d_seg_size.release(); ctx->d_payload_len.release(); ctx->d_status.release();
+    delete ctx;
+}
+
+void *lz4b200_ctx_stream(lz4b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+size_t lz4b200_max_output_size(size_t n) { return 16 + 4 + (size_t)((uint64_t)n * 110 / 100); }
+
+uint32_t lz4b200_xxh32(const uint8_t *data, size_t n, uint32_t seed)
+{
+    Xxh32 h(seed);
+    h.update(data, n);
+    return h.digest();
+}
+
+void lz4b200_xxh32_reset(lz4b200_xxh32_state *st, uint32_t seed)
+{
+    Xxh32 h(seed);
+    memcpy(st->acc, h.acc, sizeof st->acc);
+    st->fill = 0; st->seed = seed; st->total = 0;
+}
+
+void lz4b200_xxh32_update(lz4b200_xxh32_state *st, const uint8_t *data, size_t n)
+{
+    Xxh32 h(st->seed);
+    memcpy(h.acc, st->acc, sizeof st->acc); memcpy(h.buf, st->buf, 16); h.fill = st->fill; h.total = st->total;
+    h.update(data, n);
+    memcpy(st->acc, h.acc, sizeof st->acc); memcpy(st->buf, h.buf, 16); st->fill = h.fill; st->total = h.total;
+}
+
+uint32_t lz4b200_xxh32_digest(const lz4b200_xxh32_state *st)
+{
+    Xxh32 h(st->seed);
+    memcpy(h.acc, st->acc, sizeof st->acc); memcpy(h.buf, st->buf, 16); h.fill = st->fill; h.total = st->total;
+    return h.digest();
+}
+
+// ---- device batch entry points ----------------------------------------------------------------
+
+lz4b200_status lz4b200_compress_batch_device(lz4b200_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+                                             const uint32_t *d_in_len, const uint8_t *d_flags, uint8_t *d_out,
+                                             const uint64_t *d_out_off, const uint32_t *d_out_cap,
+                                             uint32_t *d_out_len, int32_t *d_status, size_t nblocks,
+                                             uint32_t max_in_len, void *stream)
+{
+    if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks && (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len || !d_status))
+        return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    BatchArgs a{d_in, d_in_off, d_in_len, d_flags, d_out, d_out_off, d_out_cap, d_out_len, d_status, nullptr,
+                (uint32_t)nblocks, nullptr};
+    return launch_compress(ctx, a, max_in_len, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+                                               const uint32_t *d_in_len, uint8_t *d_out, const uint64_t *d_out_off,
+                                               const uint32_t *d_out_cap, uint32_t *d_out_len, int32_t *d_status,
+                                               uint64_t *d_err_expected, size_t nblocks, void *stream)
+{
+    if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks && (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len || !d_status))
+        return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    BatchArgs a{d_in, d_in_off, d_in_len, nullptr, d_out, d_out_off, d_out_cap, d_out_len, d_status, d_err_expected,
+                (uint32_t)nblocks, nullptr};
+    return launch_decompress(ctx, a, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+// ---- host batch entry points --------------------------------------------------------------------
+
+lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                           const uint32_t *in_len, const uint8_t *flags, uint8_t *out,
+                                           size_t out_cap_total, uint64_t *out_off, uint32_t *out_len,
+                                           int32_t *status, size_t nblocks)
+{
+    if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks == 0) return LZ4B200_OK;
+    if (!in || !in_off || !in_len || !out || !out_off || !out_len || !status) return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint32_t nb = (uint32_t)nblocks;
+
+    // input span and padded device slots
+    uint64_t lo = ~0ull, hi = 0, slot_total = 0;
+    uint32_t max_len = 0;
+    std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
+    std::vector<uint32_t> h_cap(nb);
+    for (uint32_t b = 0; b < nb; b++) {
+        lo = std::min<uint64_t>(lo, in_off[b]);
+        hi = std::max<uint64_t>(hi, in_off[b] + in_len[b]);
+        max_len = std::max(max_len, in_len[b]);
+    }
+    for (uint32_t b = 0; b < nb; b++) {
+        h_in_off[b] = in_off[b] - lo;
+        h_slot_off[b] = slot_total;
+        size_t m = lz4b200_max_output_size(in_len[b]);
+        if (m > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+        h_cap[b] = (uint32_t)m;
+        slot_total += (m + 15) & ~size_t(15);
+    }
+    const uint64_t span = hi - lo;
+    CTX_CUDA(ctx, ctx->d_in.reserve(span + 16));
+    CTX_CUDA(ctx, ctx->d_slots.reserve(slot_total + 16));
+    CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + 1));
+    if (flags) CTX_CUDA(ctx, ctx->d_flags.reserve(nb));
+
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in + lo, span, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s));
+    if (flags) CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, flags, nb, cudaMemcpyHostToDevice, s));
+
+    BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, flags ? ctx->d_flags.p : nullptr, ctx->d_slots.p,
+                ctx->d_out_off.p, ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
+    lz4b200_status st = launch_compress(ctx, a, max_len, s);
+    if (st != LZ4B200_OK) return st;
+
+    // pack: scan the produced lengths, gather slots -> dense buffer, one D2H of exactly the payload
+    scan_sizes_kernel<<<1, 1024, 0, s>>>(ctx->d_out_len.p, ctx->d_seg_off.p, nb);
+    CTX_CUDA(ctx, cudaGetLastError());
+    CTX_CUDA(ctx, cudaMemcpyAsync(out_len, ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
+    std::vector<uint64_t> h_seg(nb + 1);
+    CTX_CUDA(ctx, cudaMemcpyAsync(h_seg.data(), ctx->d_seg_off.p, (nb + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    const uint64_t total = h_seg[nb];
+    for (uint32_t b = 0; b < nb; b++) out_off[b] = h_seg[b];
+    if (total > out_cap_total) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    CTX_CUDA(ctx, ctx->d_out.reserve(total + 16));
+    GatherArgs g{ctx->d_slots.p, nullptr, ctx->d_out_off.p, nullptr, ctx->d_out_len.p, nullptr, nullptr, nullptr,
+                 ctx->d_out.p, ctx->d_seg_off.p, nb};
+    gather_segments_kernel<<<std::min<uint32_t>(nb, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+    CTX_CUDA(ctx, cudaGetLastError());
+    CTX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                             const uint32_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                             const uint32_t *out_cap, uint32_t *out_len, int32_t *status,
+                                             uint64_t *err_expected, size_t nblocks)
+{
+    if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks == 0) return LZ4B200_OK;
+    if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len || !status)
+        return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const uint32_t nb = (uint32_t)nblocks;
+    uint64_t ilo = ~0ull, ihi = 0, olo = ~0ull, ohi = 0;
+    bool contiguous = true;
+    for (uint32_t b = 0; b < nb; b++) {
+        ilo = std::min<uint64_t>(ilo, in_off[b]); ihi = std::max<uint64_t>(ihi, in_off[b] + in_len[b]);
+        olo = std::min<uint64_t>(olo, out_off[b]); ohi = std::max<uint64_t>(ohi, out_off[b] + out_cap[b]);
+        if (b && out_off[b] != out_off[b - 1] + out_cap[b - 1]) contiguous = false;
+    }
+    std::vector<uint64_t> h_in_off(nb), h_out_off(nb);
+    for (uint32_t b = 0; b < nb; b++) { h_in_off[b] = in_off[b] - ilo; h_out_off[b] = out_off[b] - olo; }
+    CTX_CUDA(ctx, ctx->d_in.reserve(ihi - ilo + 16));
+    CTX_CUDA(ctx, ctx->d_out.reserve(ohi - olo + 16));
+    CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_expected.reserve(nb));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in + ilo, ihi - ilo, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_out_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, out_cap, nb * 4, cudaMemcpyHostToDevice, s));
+    BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_out.p, ctx->d_out_off.p,
+                ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, ctx->d_expected.p, nb, nullptr};
+    lz4b200_status st = launch_decompress(ctx, a, s);
+    if (st != LZ4B200_OK) return st;
+    CTX_CUDA(ctx, cudaMemcpyAsync(out_len, ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
+    CTX_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
+    if (err_expected)
+        CTX_CUDA(ctx, cudaMemcpyAsync(err_expected, ctx->d_expected.p, nb * 8, cudaMemcpyDeviceToHost, s));
+    if (contiguous) {
+        CTX_CUDA(ctx, cudaMemcpyAsync(out + olo, ctx->d_out.p, ohi - olo, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    } else {
+        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+        for (uint32_t b = 0; b < nb; b++)
+            if (out_len[b])
+                CTX_CUDA(ctx, cudaMemcpyAsync(out + out_off[b], ctx->d_out.p + h_out_off[b], out_len[b],
+                                              cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return LZ4B200_OK;
+}
+
+// ---- single-block host entry points -----------------------------------------------------------
+
+lz4b200_status lz4b200_compress_into(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                     size_t *written)
+{
+    if (!ctx || !written || (!in && n) || n > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (cap < lz4b200_max_output_size(n)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;     // compress.rs:338-340
+    uint64_t in_off = 0, out_off = 0;
+    uint32_t in_len = (uint32_t)n, out_len = 0;
+    int32_t status = 0;
+    static const uint8_t zero = 0;
+    lz4b200_status st = lz4b200_compress_batch_host(ctx, n ? in : &zero, &in_off, &in_len, nullptr, out, cap, &out_off,
+                                                    &out_len, &status, 1);
+    if (st != LZ4B200_OK) return st;
+    if (status != LZ4B200_OK) return (lz4b200_status)status;
+    *written = out_len;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_compress_prepend_size(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                             size_t *written)
+{
+    if (!written) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (cap < 4) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    wr32(out, (uint32_t)n);                                                              // compress.rs:633/649
+    size_t w = 0;
+    lz4b200_status st = lz4b200_compress_into(ctx, in, n, out + 4, cap - 4, &w);
+    if (st == LZ4B200_OK) *written = w + 4;
+    return st;
+}
+
+lz4b200_status lz4b200_decompress_into(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                       size_t *written, size_t *err_expected, size_t *err_actual)
+{
+    if (!ctx || !written || n > 0xffffffffull || cap > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (err_expected) *err_expected = 0;
+    if (err_actual) *err_actual = 0;
+    if (n == 0) return LZ4B200_DEC_EXPECTED_ANOTHER_BYTE;                                // decompress.rs:207-209
+    uint64_t in_off = 0, out_off = 0, expected = 0;
+    uint32_t in_len = (uint32_t)n, out_cap = (uint32_t)cap, out_len = 0;
+    int32_t status = 0;
+    uint8_t dummy = 0;
+    lz4b200_status st = lz4b200_decompress_batch_host(ctx, in, &in_off, &in_len, cap ? out : &dummy, &out_off, &out_cap,
+                                                      &out_len, &status, &expected, 1);
+    if (st != LZ4B200_OK) return st;
+    if (status != LZ4B200_OK) {
+        if (status == LZ4B200_DEC_OUTPUT_TOO_SMALL) {
+            if (err_expected) *err_expected = (size_t)expected;
+            if (err_actual) *err_actual = cap;
+        }
+        return (lz4b200_status)status;
+    }
+    *written = out_len;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_uncompressed_size(const uint8_t *in, size_t n, size_t *size)
+{
+    if (!size) return LZ4B200_INVALID_ARGUMENT;
+    if (n < 4) return LZ4B200_DEC_EXPECTED_ANOTHER_BYTE;                                 // block/mod.rs:151-157
+    *size = rd32(in);
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_decompress_size_prepended(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out,
+                                                 size_t cap, size_t *written, size_t *err_expected,
+                                                 size_t *err_actual)
+{
+    size_t want = 0;
+    if (written) *written = 0;
+    lz4b200_status st = lz4b200_uncompressed_size(in, n, &want);
+    if (st != LZ4B200_OK) return st;
+    if (cap < want) return LZ4B200_INVALID_ARGUMENT;
+    return lz4b200_decompress_into(ctx, in + 4, n - 4, out, want, written, err_expected, err_actual);
+}
+
+// ---- frame format ---------------------------------------------------------------------------------
+
+size_t lz4b200_frame_write_header(const lz4b200_frame_info *info, uint8_t *out, size_t cap)
+{
+    // FrameInfo::write — frame/header.rs:232-275
+    uint8_t buf[19];
+    size_t o = 0;
+    wr32(buf, 0x184D2204u); o = 4;
+    uint8_t flg = 0x40;
+    if (info->block_checksums) flg |= 0x10;
+    if (info->content_checksum) flg |= 0x04;
+    if (!info->linked) flg |= 0x20;
+    if (info->has_content_size) flg |= 0x08;
+    buf[o++] = flg;
+    buf[o++] = (uint8_t)(info->block_size_id << 4);
+    if (info->has_content_size) { memcpy(buf + o, &info->content_size, 8); o += 8; }
+    buf[o] = (uint8_t)(lz4b200_xxh32(buf + 4, o - 4, 0) >> 8);
+    o++;
+    if (cap < o) return 0;
+    memcpy(out, buf, o);
+    return o;
+}
+
+size_t lz4b200_frame_blocks_bound(size_t in_len, size_t block_size)
+{
+    size_t nb = block_size ? (in_len + block_size - 1) / block_size : 0;
+    return in_len + nb * 4;
+}
+
+size_t lz4b200_frame_bound(size_t n, const lz4b200_frame_info *info)
+{
+    int id = info && info->block_size_id ? info->block_size_id : 4;
+    size_t bs = block_size_bytes(id);
+    if (!bs) bs = 64u << 10;
+    size_t nb = (n + bs - 1) / bs;
+    return 19 + n + nb * 8 + 8;
+}
+
+lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx, const uint8_t *d_in, size_t in_len,
+                                                    size_t block_size, uint64_t first_block, uint8_t *d_out,
+                                                    size_t out_cap, uint64_t *d_total, uint32_t *d_block_sizes,
+                                                    void *stream)
+{
+    if (!ctx || !block_size || block_size > (8u << 20)) return LZ4B200_INVALID_ARGUMENT;
+    const size_t nblocks = (in_len + block_size - 1) / block_size;
+    if (nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (out_cap < lz4b200_frame_blocks_bound(in_len, block_size)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t nb = (uint32_t)nblocks;
+    if (nb == 0) {
+        if (d_total) CTX_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, s));
+        return LZ4B200_OK;
+    }
+    const size_t slot = (lz4b200_max_output_size(block_size) + 15) & ~size_t(15);
+    CTX_CUDA(ctx, ctx->d_slots.reserve(slot * nb + 16));
+    CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_flags.reserve(nb)); CTX_CUDA(ctx, ctx->d_pick.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_info.reserve(nb)); CTX_CUDA(ctx, ctx->d_seg_size.reserve(nb));
+    CTX_CUDA(ctx, ctx->d_payload_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + 1));
+
+    make_uniform_desc_kernel<<<(nb + 255) / 256, 256, 0, s>>>(in_len, (uint32_t)block_size, slot, first_block,
+                                                             fresh_period(block_size), nb, ctx->d_in_off.p,
+                                                             ctx->d_in_len.p, ctx->d_out_off.p, ctx->d_out_cap.p,
+                                                             ctx->d_flags.p);
+    CTX_CUDA(ctx, cudaGetLastError());
+    BatchArgs a{d_in, ctx->d_in_off.p, ctx->d_in_len.p, ctx->d_flags.p, ctx->d_slots.p, ctx->d_out_off.p,
+                ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
+    lz4b200_status st = launch_compress(ctx, a, (uint32_t)std::min<size_t>(block_size, in_len), s);
+    if (st != LZ4B200_OK) return st;
+    frame_block_info_kernel<<<(nb + 255) / 256, 256, 0, s>>>(ctx->d_out_len.p, ctx->d_in_len.p, nb, ctx->d_info.p,
+                                                            ctx->d_pick.p, ctx->d_seg_size.p, ctx->d_payload_len.p);
+    CTX_CUDA(ctx, cudaGetLastError());
+    scan_sizes_kernel<<<1, 1024, 0, s>>>(ctx->d_seg_size.p, ctx->d_seg_off.p, nb);
+    CTX_CUDA(ctx, cudaGetLastError());
+    GatherArgs g{ctx->d_slots.p, d_in, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p, ctx->d_payload_len.p,
+                 ctx->d_pick.p, ctx->d_info.p, d_out, ctx->d_seg_off.p, nb};
+    gather_segments_kernel<<<std::min<uint32_t>(nb, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+    CTX_CUDA(ctx, cudaGetLastError());
+    if (d_total) CTX_CUDA(ctx, cudaMemcpyAsync(d_total, ctx->d_seg_off.p + nb, 8, cudaMemcpyDeviceToDevice, s));
+    if (d_block_sizes)
+        CTX_CUDA(ctx, cudaMemcpyAsync(d_block_sizes, ctx->d_seg_size.p, nb * 4, cudaMemcpyDeviceToDevice, s));
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_frame_compress(lz4b200_ctx *ctx, const uint8_t *in, size_t n, const lz4b200_frame_info *info_in,
+                                      size_t first_write_len, uint8_t *out, size_t cap, size_t *written)
+{
+    if (!ctx || !info_in || !out || !written || (!in && n)) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    lz4b200_frame_info info = *info_in;
+    if (info.linked) return LZ4B200_FRAME_LINKED_UNSUPPORTED;
+    if (info.block_size_id == 0) info.block_size_id = auto_block_size_id(first_write_len);   // compress.rs:236-238
+    if (info.block_size_id < 4 || info.block_size_id > 7) return LZ4B200_INVALID_ARGUMENT;
+    if (info.has_content_size && info.content_size != n) return LZ4B200_FRAME_CONTENT_LENGTH; // compress.rs:212-219
+    const size_t bs = block_size_bytes(info.block_size_id);
+    if (cap < lz4b200_frame_bound(n, &info)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+
+    size_t o = lz4b200_frame_write_header(&info, out, cap);
+    const size_t nblocks = (n + bs - 1) / bs;
+    if (nblocks) {
+        const size_t bound = lz4b200_frame_blocks_bound(n, bs);
+        CTX_CUDA(ctx, ctx->d_in.reserve(n + 16));
+        CTX_CUDA(ctx, ctx->d_out.reserve(bound + 16));
+        CTX_CUDA(ctx, ctx->d_off_b.reserve(1));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in, n, cudaMemcpyHostToDevice, s));
+        lz4b200_status st = lz4b200_frame_compress_blocks_device(ctx, ctx->d_in.p, n, bs, 0, ctx->d_out.p, bound,
+                                                                 ctx->d_off_b.p, nullptr, s);
+        if (st != LZ4B200_OK) return st;
+        uint64_t total = 0;
+        CTX_CUDA(ctx, cudaMemcpyAsync(&total, ctx->d_off_b.p, 8, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+        if (!info.block_checksums) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(out + o, ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaStreamSynchronize(s));
+            o += total;
+        } else {
+            // block checksum = XXH32 of the payload as written (frame/compress.rs:313-316): host-side walk
+            std::vector<uint8_t> tmp(total);
+            CTX_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaStreamSynchronize(s));
+            size_t p = 0;
+            while (p < total) {
+                uint32_t word = rd32(tmp.data() + p);
+                size_t len = word & 0x7fffffffu;
+                memcpy(out + o, tmp.data() + p, 4 + len);
+                wr32(out + o + 4 + len, lz4b200_xxh32(tmp.data() + p + 4, len, 0));
+                o += 8 + len; p += 4 + len;
+            }
+        }
+    }
+    wr32(out + o, 0); o += 4;                                                            // EndMark: compress.rs:221-223
+    if (info.content_checksum) { wr32(out + o, lz4b200_xxh32(in, n, 0)); o += 4; }       // compress.rs:224-227
+    *written = o;
+    return LZ4B200_OK;
+}
+
+namespace {
+
+struct FrameBlockRef {
+    uint64_t payload_off;     // into the input buffer
+    uint32_t payload_len;
+    uint32_t max_out;         // block size of the owning frame
+    bool stored;
+    uint32_t frame_idx;
+};
+struct FrameRef {
+    uint32_t first_block, nblocks;
+    bool has_size, has_checksum, closed;
+    uint64_t content_size;
+    uint32_t content_checksum;
+};
+
+}  // namespace
+
+lz4b200_status lz4b200_frame_decoded_bound(const uint8_t *in, size_t n, size_t *bound)
+{
+    if (!bound || (!in && n)) return LZ4B200_INVALID_ARGUMENT;
+    size_t ip = 0, total = 0;
+    while (ip + 4 <= n) {
+        uint32_t magic = rd32(in + ip);
+        size_t bs; unsigned flg = 0x20;
+        bool sized = false; uint64_t csize = 0;
+        if (magic == 0x184C2102u) { ip += 4; bs = 8u << 20; }
+        else {
+            if (n - ip < 7 || magic != 0x184D2204u) break;
+            flg = in[ip + 4];
+            int id = (in[ip + 5] >> 4) & 7;
+            bs = block_size_bytes(id);
+            if (!bs) break;
+            size_t need = 7 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0);
+            if (n - ip < need) break;
+            if (flg & 8) { memcpy(&csize, in + ip + 6, 8); sized = true; }
+            ip += need;
+        }
+        size_t frame_total = 0;
+        for (;;) {
+            if (n - ip < 4) { ip = n; break; }
+            uint32_t word = rd32(in + ip); ip += 4;
+            if (word == 0) { if (flg & 4) ip += 4; break; }
+            size_t len = word & 0x7fffffffu;
+            frame_total += (word & 0x80000000u) ? len : bs;
+            ip += len + ((flg & 0x10) ? 4 : 0);
+            if (ip > n) { ip = n; break; }
+        }
+        total += sized ? std::min<uint64_t>(csize, frame_total) : frame_total;
+    }
+    *bound = total;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                        size_t *written, int *block_status)
+{
+    if (!ctx || !written || (!in && n) || (!out && cap)) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (block_status) *block_status = 0;
+
+    // ---- host walk: frame headers and BlockInfo chain (frame/decompress.rs:109-342) ----------
+    std::vector<FrameBlockRef> blocks;
+    std::vector<FrameRef> frames;
+    lz4b200_status walk_err = LZ4B200_OK;
+    size_t ip = 0;
+    while (ip < n && walk_err == LZ4B200_OK) {
+        if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+        uint32_t magic = rd32(in + ip);
+        size_t bs; unsigned flg = 0x20;
+        FrameRef fr{(uint32_t)blocks.size(), 0, false, false, false, 0, 0};
+        if (magic == 0x184C2102u) {                         // legacy frame: header.rs:285-291
+            ip += 4; bs = 8u << 20;
+        } else {
+            if (n - ip < 7) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+            if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) { walk_err = LZ4B200_FRAME_SKIPPABLE; break; }
+            if (magic != 0x184D2204u) { walk_err = LZ4B200_FRAME_WRONG_MAGIC; break; }
+            const size_t h = ip + 4;
+            flg = in[h];
+            const uint8_t bd = in[h + 1];
+            const size_t need = 7 + ((flg & 0x08) ? 8 : 0) + ((flg & 0x01) ? 4 : 0);
+            if (n - ip < need) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+            if ((flg & 0xC0) != 0x40) { walk_err = LZ4B200_FRAME_UNSUPPORTED_VERSION; break; }
+            if ((flg & 0x02) || (bd & 0x8F)) { walk_err = LZ4B200_FRAME_RESERVED_BITS; break; }
+            const int id = (bd >> 4) & 7;
+            if (id < 4) { walk_err = LZ4B200_FRAME_UNSUPPORTED_BLOCKSIZE; break; }
+            bs = block_size_bytes(id);
+            size_t o = h + 2;
+            if (flg & 0x08) { memcpy(&fr.content_size, in + o, 8); fr.has_size = true; o += 8; }
+            if (flg & 0x01) o += 4;
+            if ((uint8_t)(lz4b200_xxh32(in + h, o - h, 0) >> 8) != in[o]) { walk_err = LZ4B200_FRAME_HEADER_CHECKSUM; break; }
+            if (flg & 0x01) { walk_err = LZ4B200_FRAME_DICTIONARY; break; }
+            if (!(flg & 0x20)) { walk_err = LZ4B200_FRAME_LINKED_UNSUPPORTED; break; }
+            ip = o + 1;
+        }
+        const uint32_t fidx = (uint32_t)frames.size();
+        for (;;) {
+            if (n - ip < 4) { ip = n; break; }              // EOF where a BlockInfo is due: decompress.rs:236-243
+            const uint32_t word = rd32(in + ip); ip += 4;
+            if (word == 0) {                                 // EndMark
+                fr.closed = true;
+                if (flg & 0x04) {
+                    if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+                    fr.has_checksum = true; fr.content_checksum = rd32(in + ip); ip += 4;
+                }
+                break;
+            }
+            const size_t len = word & 0x7fffffffu;
+            if (len > bs) { walk_err = LZ4B200_FRAME_BLOCK_TOO_BIG; break; }
+            if (n - ip < len) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+            const size_t payload = ip; ip += len;
+            if (flg & 0x10) {
+                if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
+                if (rd32(in + ip) != lz4b200_xxh32(in + payload, len, 0)) { walk_err = LZ4B200_FRAME_BLOCK_CHECKSUM; break; }
+                ip += 4;
+            }
+            blocks.push_back({payload, (uint32_t)len, (uint32_t)bs, (word & 0x80000000u) != 0, fidx});
+            fr.nblocks++;
+        }
+        frames.push_back(fr);
+    }
+
+    // ---- decode every block seen before the walk stopped ---------------------------------------
+    const uint32_t nb = (uint32_t)blocks.size();
+    std::vector<uint32_t> produced(nb, 0);
+    std::vector<int32_t> status(nb, 0);
+    std::vector<uint64_t> seg(nb + 1, 0);
+    if (nb) {
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
+        std::vector<uint32_t> h_in_len(nb), h_cap(nb);
+        std::vector<uint8_t> h_pick(nb);
+        uint64_t slot_total = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            h_in_off[b] = blocks[b].payload_off;
+            h_in_len[b] = blocks[b].stored ? 0 : blocks[b].payload_len;   // stored blocks are only gathered
+            h_pick[b] = blocks[b].stored ? 1 : 0;
+            h_slot_off[b] = slot_total;
+            h_cap[b] = blocks[b].stored ? 0 : blocks[b].max_out;
+            slot_total += h_cap[b];
+        }
+        CTX_CUDA(ctx, ctx->d_in.reserve(n + 16));
+        CTX_CUDA(ctx, ctx->d_slots.reserve(slot_total + 16));
+        CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
+        CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
+        CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
+        CTX_CUDA(ctx, ctx->d_pick.reserve(nb)); CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + 1));
+        CTX_CUDA(ctx, ctx->d_payload_len.reserve(nb));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in, n, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, h_in_len.data(), nb * 4, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pick.p, h_pick.data(), nb, cudaMemcpyHostToDevice, s));
+        BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_slots.p, ctx->d_out_off.p,
+                    ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
+        lz4b200_status st = launch_decompress(ctx, a, s);
+        if (st != LZ4B200_OK) return st;
+        CTX_CUDA(ctx, cudaMemcpyAsync(produced.data(), ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
+        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+
+        // first failing block (stream order) wins over anything the walk found later
+        uint32_t good = nb;
+        for (uint32_t b = 0; b < nb; b++) {
+            if (blocks[b].stored) { produced[b] = blocks[b].payload_len; status[b] = 0; continue; }
+            if (status[b] != 0) { good = b; break; }
+        }
+        uint64_t total = 0;
+        for (uint32_t b = 0; b < good; b++) { seg[b] = total; total += produced[b]; }
+        seg[good] = total;
+        const bool overflow = total > cap;
+        if (!overflow && good) {
+            CTX_CUDA(ctx, ctx->d_out.reserve(total + 16));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_seg_off.p, seg.data(), (good + 1) * 8, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_payload_len.p, produced.data(), good * 4, cudaMemcpyHostToDevice, s));
+            GatherArgs g{ctx->d_slots.p, ctx->d_in.p, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p,
+                         ctx->d_payload_len.p, ctx->d_pick.p, nullptr, ctx->d_out.p, ctx->d_seg_off.p, good};
+            gather_segments_kernel<<<std::min<uint32_t>(good, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+            CTX_CUDA(ctx, cudaGetLastError());
+            CTX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaStreamSynchronize(s));
+        }
+        if (overflow) return LZ4B200_FRAME_OUTPUT_FULL;
+        *written = total;
+        if (good < nb) {
+            if (block_status) *block_status = status[good];
+            return LZ4B200_FRAME_DECOMPRESSION_ERROR;
+        }
+    }
+    if (walk_err != LZ4B200_OK) return walk_err;
+
+    // ---- per-frame content size / checksum (decompress.rs:312-331) -----------------------------
+    for (const FrameRef &fr : frames) {
+        if (!fr.closed) continue;
+        uint64_t begin = fr.nblocks ? seg[fr.first_block] : 0, len = 0;
+        for (uint32_t b = fr.first_block; b < fr.first_block + fr.nblocks; b++) len += produced[b];
+        if (fr.has_size && len != fr.content_size) return LZ4B200_FRAME_CONTENT_LENGTH;
+        if (fr.has_checksum && lz4b200_xxh32(out + begin, len, 0) != fr.content_checksum)
+            return LZ4B200_FRAME_CONTENT_CHECKSUM;
+    }
+    return LZ4B200_OK;
+}
+
+}  // extern "C"

@@ -84,7 +84,7 @@ def lib():
         for name in ("lz4o_compress_batch", "lz4o_decompress_batch"):
             f = getattr(L, name)
             f.restype = None
-            f.argtypes = [u8p] * 9 + [sz, C.c_int]
+            f.argtypes = [u8p] * 8 + [sz, C.c_int]
         _lib = L
     return _lib
 
