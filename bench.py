@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — LZ4 block compress+decompress throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference arm: CPU path on host cores
+
+Workload (BASELINE config 2): 16 384 independent 64 KiB blocks cut from compression_66k_JSON.txt tiled to
+1 GiB, block format.  One STEP = compress all blocks, then decompress all of them (per rank).  N > 1 shards
+blocks across ranks (every rank owns its own 16 384 blocks: weak scaling, no data-path collective; the
+frame-mode gather of compressed chunks is measured separately with --workload frame).
+
+value      = uncompressed MiB per second of the whole job (all ranks) over the compress+decompress step,
+             inputs resident in HBM, timed with CUDA events, max over ranks.
+e2e        = the same metric through the host-pointer C-ABI calls, H2D/D2H copies inside the timed region.
+roofline   = dominant kernel (compress) against the measured HBM copy peak; the decompress kernel's roofline is
+             reported beside it.
+cpu_baseline = the C oracle (a restatement of lz4_flex's algorithm; Rust is not available) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 65536
+NBLOCKS_DEFAULT = 16384
+FIXTURE = "compression_66k_JSON.txt"
+METRIC = "LZ4 block MiB/s (compress+decompress) at 1/2/4/8 B200 vs CPU; % HBM peak"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(nblocks: int, rank: int):
+    from lz4_flex_b200 import corpus
+    total = nblocks * BLOCK
+    src = np.frombuffer(corpus.load(FIXTURE), dtype=np.uint8)
+    # rank r continues the tiling where rank r-1 stopped, so every rank has distinct block phases
+    start = (rank * total) % src.size
+    reps = -(-(total + start) // src.size)
+    data = np.tile(src, reps)[start:start + total]
+    return np.ascontiguousarray(data)
+
+
+def cpu_arm(data: np.ndarray, nblocks: int, threads: int, repeats: int):
+    """Oracle compress+decompress of `nblocks` blocks on `threads` host threads; best of `repeats`."""
+    import oracle
+    slot = 72112
+    offs = np.arange(nblocks, dtype=np.uint64) * BLOCK
+    lens = np.full(nblocks, BLOCK, dtype=np.uint32)
+    soff = np.arange(nblocks, dtype=np.uint64) * slot
+    scap = np.full(nblocks, slot, dtype=np.uint32)
+    comp = np.zeros(nblocks * slot, dtype=np.uint8)
+    back = np.zeros(nblocks * BLOCK, dtype=np.uint8)
+    comp[::4096] = 1; back[::4096] = 1                       # pre-fault
+    best = (1e30, 1e30)
+    clen = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        clen, st = oracle.compress_batch(data, offs, lens, comp, soff, scap, threads)
+        t1 = time.perf_counter()
+        olen, st2 = oracle.decompress_batch(comp, soff, clen, back, offs, lens, threads)
+        t2 = time.perf_counter()
+        assert not st.any() and not st2.any()
+        if (t2 - t0) < sum(best):
+            best = (t1 - t0, t2 - t1)
+    assert np.array_equal(back[: nblocks * BLOCK], data[: nblocks * BLOCK])
+    mib = nblocks * BLOCK / 2**20
+    return {"compress_mibs": mib / best[0], "decompress_mibs": mib / best[1], "roundtrip_mibs": mib / sum(best),
+            "ratio": float(clen.astype(np.uint64).sum()) / (nblocks * BLOCK)}
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path on all host cores (oracle port; no Rust toolchain)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_blocks = min(args.blocks, 4096)
+    data = build_workload(sample_blocks, 0)
+    for _ in range(args.warmup):
+        cpu_arm(data, sample_blocks, threads, 1)
+    t0 = time.perf_counter()
+    res = [cpu_arm(data, sample_blocks, threads, 1) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    val = float(np.median([r["roundtrip_mibs"] for r in res]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "MiB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": f"{FIXTURE} tiled (deterministic corpus fixture, BASELINE config 2)",
+        "config": {"workload": f"{args.blocks} x 64 KiB JSON blocks, block format, compress+decompress",
+                   "block_bytes": BLOCK, "blocks_per_gpu": args.blocks},
+        "cpu_baseline": {"value": val, "unit": "MiB/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_blocks} of the {args.blocks} blocks per step, compress+decompress, "
+                                   f"{threads} threads, one block per task",
+                         "compress_mibs": float(np.median([r['compress_mibs'] for r in res])),
+                         "decompress_mibs": float(np.median([r['decompress_mibs'] for r in res]))},
+        "e2e": {"value": val, "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lz4_flex_b200 import block
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nb = args.blocks
+    data = build_workload(nb, rank)
+    ctx = block.Context(local)
+    slot = 72112                                        # get_maximum_output_size(65536) = 72109, 16-byte aligned
+    offs = np.arange(nb, dtype=np.uint64) * BLOCK
+    lens = np.full(nb, BLOCK, dtype=np.uint32)
+    soff = np.arange(nb, dtype=np.uint64) * slot
+    scap = np.full(nb, slot, dtype=np.uint32)
+
+    h_in = torch.empty(nb * BLOCK, dtype=torch.uint8).pin_memory()
+    h_in.numpy()[:] = data
+    d_in = h_in.to(dev, non_blocking=True)
+    d_comp = torch.zeros(nb * slot, dtype=torch.uint8, device=dev)
+    d_back = torch.zeros(nb * BLOCK, dtype=torch.uint8, device=dev)
+    enc = block.DeviceBatch(offs, lens, soff, scap, None, dev)
+    dec = block.DeviceBatch(soff, lens, offs, lens, None, dev)
+    dec.in_len = enc.out_len                             # decompress reads exactly what compress produced
+    torch.cuda.synchronize()
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        enc.compress(d_in, d_comp, ctx)
+        if events is not None:
+            events[1].record()
+        dec.decompress(d_comp, d_back, ctx)
+        if events is not None:
+            events[2].record()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    # verification outside the timed region: statuses, exact round trip, oracle bytes on a sample
+    assert int(enc.status.abs().sum()) == 0 and int(dec.status.abs().sum()) == 0, "block status != OK"
+    assert torch.equal(d_back, d_in), "round trip differs from the input"
+    clen = enc.out_len.cpu().numpy().astype(np.uint64)
+    comp_bytes = int(clen.sum())
+    if rank == 0:
+        import oracle
+        for b in (0, 1, nb // 2, nb - 1):
+            got = d_comp[b * slot: b * slot + int(clen[b])].cpu().numpy().tobytes()
+            assert got == oracle.compress_block(data[b * BLOCK:(b + 1) * BLOCK]), f"block {b} differs from the oracle"
+
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_start.elapsed_time(t_end)
+    t_c = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_d = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, t_c, t_d], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, t_c, t_d = [float(x) for x in t.cpu()]
+
+    if args.quick:                                      # tuning aid: device-timed kernels only
+        if rank == 0:
+            print(json.dumps({"quick": True, "compress_ms": t_c, "decompress_ms": t_d,
+                              "ms_per_step": elapsed_ms / args.steps}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies inside the timed region) ----
+    h_comp = torch.empty(comp_bytes + 4096, dtype=torch.uint8).pin_memory()
+    h_back = torch.empty(nb * BLOCK, dtype=torch.uint8).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_t = []
+    for it in range(2 + e2e_steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out, ooff, olen = block.compress_batch(h_in.numpy(), offs, lens, None, out=h_comp.numpy(), ctx=ctx)
+        block.decompress_batch(out, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if it >= 2:
+            e2e_t.append(dt)
+    assert np.array_equal(h_back.numpy(), data)
+    e2e_s = float(np.mean(e2e_t))
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.cpu()[0])
+    desc_bytes = nb * (8 + 4 + 8 + 4)
+    h2d = nb * BLOCK + comp_bytes + 2 * desc_bytes
+    d2h = comp_bytes + nb * BLOCK + nb * (4 + 4 + 8) + nb * (4 + 4 + 8)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    mib_rank = nb * BLOCK / 2**20
+    ms_per_step = elapsed_ms / args.steps
+    value = world * mib_rank / (ms_per_step / 1e3)
+    peak, peak_src = measured_peaks()
+    alg_bytes = nb * BLOCK + comp_bytes                 # uncompressed + compressed, either direction
+    ach_c = alg_bytes / (t_c / 1e3) / 1e9
+    ach_d = alg_bytes / (t_d / 1e3) / 1e9
+
+    # CPU baseline on this box's host cores (bounded sample)
+    threads = os.cpu_count() or 1
+    sample_blocks = min(nb, 4096)
+    cpu_all = cpu_arm(data, sample_blocks, threads, 3)
+    cpu_one = cpu_arm(data, min(nb, 512), 1, 2)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MiB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8",
+        "data": f"{FIXTURE} tiled (deterministic corpus fixture, BASELINE config 2); inputs larger than L2",
+        "config": {"workload": f"{nb} x 64 KiB JSON blocks per GPU (1 GiB), block format, compress+decompress, "
+                               f"byte-identical to the oracle", "block_bytes": BLOCK, "blocks_per_gpu": nb,
+                   "l2_policy": "inputs (1 GiB in, 0.24 GiB compressed, 1 GiB out per step) larger than the 126 MB L2",
+                   "ratio": comp_bytes / (nb * BLOCK)},
+        "compress_mibs": world * mib_rank / (t_c / 1e3), "decompress_mibs": world * mib_rank / (t_d / 1e3),
+        "compress_ms": t_c, "decompress_ms": t_d,
+        "roofline": {"kernel": "lz4_compress_blocks<u16,4>", "bound": "hbm", "achieved": ach_c, "peak": peak,
+                     "unit": "GB/s", "frac": ach_c / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes},
+        "roofline_decompress": {"kernel": "lz4_decompress_blocks", "bound": "hbm", "achieved": ach_d, "peak": peak,
+                                "unit": "GB/s", "frac": ach_d / peak, "traffic": None, "peak_source": peak_src,
+                                "algorithmic_bytes_per_launch": alg_bytes},
+        "cpu_baseline": {"value": cpu_all["roundtrip_mibs"], "unit": "MiB/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_blocks} of the {nb} blocks, compress+decompress, best of 3, "
+                                   f"{threads} threads (one block per task)",
+                         "compress_mibs": cpu_all["compress_mibs"], "decompress_mibs": cpu_all["decompress_mibs"],
+                         "single_thread": {"compress_mibs": cpu_one["compress_mibs"],
+                                           "decompress_mibs": cpu_one["decompress_mibs"]}},
+        "e2e": {"value": world * mib_rank / e2e_s, "unit": "MiB/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
+                "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers)"},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blocks", type=int, default=NBLOCKS_DEFAULT, help="64 KiB blocks per GPU")
+    ap.add_argument("--quick", action="store_true", help="kernel timings only (tuning aid; not a bench line)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

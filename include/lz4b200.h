@@ -12,7 +12,10 @@
  *   - every function returns an lz4b200_status; bad *data* is never a crash, always a code
  *     (mirrors Result<_, DecompressError/CompressError>, src/block/mod.rs:82-106).
  *   - "device" variants take device pointers and a CUDA stream (cudaStream_t passed as
- *     void*), enqueue work and return without synchronising.  "host" variants take host
+ *     void*; NULL is the legacy default stream, lz4b200_ctx_stream() the context's own),
+ *     enqueue work and return without synchronising.  Launches of one context must be
+ *     stream-ordered with respect to each other (they share the context's ticket counters
+ *     and scratch).  "host" variants take host
  *     pointers, stage through pinned memory and return when the result is in the caller's
  *     buffer.
  *   - all functions are thread-safe for distinct contexts; one context may be used by one

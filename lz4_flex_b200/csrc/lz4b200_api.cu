@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -247,6 +248,9 @@ struct lz4b200_ctx {
     cudaStream_t stream = nullptr;
     uint32_t *d_tickets = nullptr;            // 3 x {next, retired}
     int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
+    int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
+    int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
+    int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32 (tuning aid)
     std::string last_error;
 
     // scratch for host-pointer and frame entry points
@@ -279,16 +283,40 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+template <int G>
+lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStream_t s)
+{
+    const uint32_t per_cta = kDecWarpsPerCta * (32 / G);
+    uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * (ctx->dec_ctas_override ? ctx->dec_ctas_override : 16)));
+    if (ctx->dec_batched) lz4_decompress_blocks<G, 1><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    else lz4_decompress_blocks<G, 0><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    CTX_CUDA(ctx, cudaGetLastError());
+    return LZ4B200_OK;
+}
+
+// Lanes per block: with few blocks every block gets a whole warp (widest copies, most parallel
+// chains); with many blocks narrower groups cut the warp-instructions per sequence.
+int pick_dec_group(const lz4b200_ctx *ctx, uint32_t nblocks)
+{
+    if (ctx->dec_group_override) return ctx->dec_group_override;
+    const uint32_t warps = (uint32_t)(ctx->sm_count * ctx->dec_ctas_per_sm * kDecWarpsPerCta);
+    if (nblocks >= warps * 2) return 8;
+    if (nblocks >= warps) return 16;
+    return 32;
+}
+
 lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     a.tickets = ctx->d_tickets;
-    uint32_t want = (a.nblocks + kDecWarpsPerCta - 1) / kDecWarpsPerCta;
-    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->dec_ctas_per_sm));
-    lz4_decompress_blocks<<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
-    CTX_CUDA(ctx, cudaGetLastError());
-    return LZ4B200_OK;
+    switch (pick_dec_group(ctx, a.nblocks)) {
+    case 4: return launch_decompress_g<4>(ctx, a, s);
+    case 8: return launch_decompress_g<8>(ctx, a, s);
+    case 16: return launch_decompress_g<16>(ctx, a, s);
+    default: return launch_decompress_g<32>(ctx, a, s);
+    }
 }
 
 lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s)
@@ -367,7 +395,7 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
               ctx->check(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tickets), 8 * sizeof(uint32_t)), "tickets") &&
               ctx->check(cudaMemset(ctx->d_tickets, 0, 8 * sizeof(uint32_t)), "tickets memset");
     if (ok) {
-        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks,
+        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0>,
                                                                       kDecWarpsPerCta * 32, 0), "occupancy dec") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                             &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
@@ -380,6 +408,12 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
         lz4b200_ctx_destroy(ctx);
         return LZ4B200_CUDA_ERROR;
+    }
+    if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
+    if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
+    if (const char *g = getenv("LZ4B200_DEC_GROUP")) {
+        int v = atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) ctx->dec_group_override = v;
     }
     *out = ctx;
     return LZ4B200_OK;
@@ -446,7 +480,7 @@ lz4b200_status lz4b200_compress_batch_device(lz4b200_ctx *ctx, const uint8_t *d_
     DeviceGuard guard(ctx->device);
     BatchArgs a{d_in, d_in_off, d_in_len, d_flags, d_out, d_out_off, d_out_cap, d_out_len, d_status, nullptr,
                 (uint32_t)nblocks, nullptr};
-    return launch_compress(ctx, a, max_in_len, stream ? (cudaStream_t)stream : ctx->stream);
+    return launch_compress(ctx, a, max_in_len, (cudaStream_t)stream);
 }
 
 lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
@@ -460,7 +494,7 @@ lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *
     DeviceGuard guard(ctx->device);
     BatchArgs a{d_in, d_in_off, d_in_len, nullptr, d_out, d_out_off, d_out_cap, d_out_len, d_status, d_err_expected,
                 (uint32_t)nblocks, nullptr};
-    return launch_decompress(ctx, a, stream ? (cudaStream_t)stream : ctx->stream);
+    return launch_decompress(ctx, a, (cudaStream_t)stream);
 }
 
 // ---- host batch entry points --------------------------------------------------------------------
@@ -718,7 +752,7 @@ lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx, const uint
     if (nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
     if (out_cap < lz4b200_frame_blocks_bound(in_len, block_size)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     const uint32_t nb = (uint32_t)nblocks;
     if (nb == 0) {
         if (d_total) CTX_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, s));

@@ -90,9 +90,13 @@ struct WordView {
 };
 
 // =============================================================================================
-// K2: decode one block with one warp.
-// Semantics = the checked path of decompress_internal (decompress.rs:330-444): same bytes,
-// same first error, same OutputTooSmall{expected, actual} fields.
+// K2: decode.  A block is decoded by a GROUP of G lanes (G = 32, 16, 8 or 4; 32/G blocks per warp).
+// Every lane of a group walks the token chain redundantly (uniform within the group, broadcast loads)
+// and the G lanes share the byte copies.  Narrow groups trade copy width for fewer warp-instructions
+// per sequence: the parse is ~60 instructions whatever G is, so 32/G blocks per warp-instruction
+// stream divide the issue cost per sequence, which is what bounds this kernel.
+// Semantics = the checked path of decompress_internal (decompress.rs:330-444): same bytes, same
+// first error, same OutputTooSmall{expected, actual} fields.
 // =============================================================================================
 struct DecResult {
     uint32_t written;
@@ -100,29 +104,23 @@ struct DecResult {
     uint64_t expected;
 };
 
-// out[op .. op+len) = src[ip .. ip+len)   (compressed stream -> output; never overlaps)
-__device__ __forceinline__ void copy_literals(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t len,
-                                              uint32_t lane)
-{
-    for (uint32_t i = lane; i < len; i += 32) dst[i] = __ldg(src + i);
-}
-
-// out[op .. op+len) = out[op-dist .. ) with LZ77 byte-serial semantics (duplicate(),
-// duplicate_overlapping(): decompress.rs:11-82; offset 1 = run fill, decompress_safe.rs:311-313).
-__device__ __forceinline__ void copy_match(uint8_t *dst, uint32_t dist, uint32_t len, uint32_t lane)
+// out[0..len) = out[-dist ..) with LZ77 byte-serial semantics (duplicate(), duplicate_overlapping():
+// decompress.rs:11-82; offset 1 = run fill, decompress_safe.rs:311-313).
+template <int G>
+__device__ __forceinline__ void copy_match(uint8_t *dst, uint32_t dist, uint32_t len, uint32_t sub, uint32_t gmask)
 {
     const uint8_t *from = dst - dist;
     if (dist >= len) {                       // source entirely older than this match
-        for (uint32_t i = lane; i < len; i += 32) dst[i] = from[i];
-    } else if (dist >= 32) {                 // each 32-byte step only needs earlier steps
-        for (uint32_t base = 0; base < len; base += 32) {
-            uint32_t i = base + lane;
+        for (uint32_t i = sub; i < len; i += G) dst[i] = from[i];
+    } else if (dist >= (uint32_t)G) {        // each G-byte step only needs earlier steps
+        for (uint32_t base = 0; base < len; base += G) {
+            uint32_t i = base + sub;
             if (i < len) dst[i] = from[i];
-            __syncwarp();
+            __syncwarp(gmask);
         }
-    } else {                                 // period < 32: every byte is a copy of the seed period
-        uint32_t r = lane % dist, step = 32u % dist;
-        for (uint32_t i = lane; i < len; i += 32) {
+    } else {                                 // period < G: every byte is a copy of the seed period
+        uint32_t r = sub % dist, step = (uint32_t)G % dist;
+        for (uint32_t i = sub; i < len; i += G) {
             dst[i] = from[r];
             r += step;
             if (r >= dist) r -= dist;
@@ -130,77 +128,208 @@ __device__ __forceinline__ void copy_match(uint8_t *dst, uint32_t dist, uint32_t
     }
 }
 
-__device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                               uint32_t cap)
+// One sequence with every check, byte loads only.  Used for the last bytes of a stream, for long
+// length encodings and for anything that might fail.  Returns 0 = continue, 1 = stream finished OK,
+// 2 = error (r.status set).
+template <int G>
+__device__ __forceinline__ int decode_sequence_checked(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
+                                                    uint32_t cap, uint32_t &ip_io, uint32_t &op_io, uint32_t sub,
+                                                    uint32_t gmask, DecResult &r)
 {
-    const uint32_t lane = lane_id();
+    uint32_t ip = ip_io, op = op_io;
+    const uint32_t tok = __ldg(src + ip++);
+    uint64_t lit = tok >> 4;
+    if (lit == 15) {                                           // read_integer_ptr: decompress.rs:126-157
+        for (;;) {
+            if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return 2; }
+            uint32_t b = __ldg(src + ip++);
+            lit += b;
+            if (b != 255) break;
+        }
+    }
+    if (lit) {
+        if (lit > (uint64_t)(n - ip)) { r.status = LZ4B200_DEC_LITERAL_OUT_OF_BOUNDS; return 2; }   // :346
+        if (lit > (uint64_t)(cap - op)) {                                                           // :349-354
+            r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + lit; return 2;
+        }
+        for (uint32_t i = sub; i < (uint32_t)lit; i += G) dst[op + i] = __ldg(src + ip + i);
+        ip += (uint32_t)lit; op += (uint32_t)lit;
+    }
+    if (ip >= n) { ip_io = ip; op_io = op; return 1; }         // the stream ends after literals: :366
+    if (n - ip < 2) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return 2; }                   // :373
+    const uint32_t dist = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
+    ip += 2;
+    if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return 2; }                               // :161-173
+    uint64_t mlen = 4u + (tok & 15u);
+    if (mlen == 19) {
+        for (;;) {
+            if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return 2; }
+            uint32_t b = __ldg(src + ip++);
+            mlen += b;
+            if (b != 255) break;
+        }
+    }
+    if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return 2; }                      // :399
+    if (mlen > (uint64_t)(cap - op)) {                                                             // :402-406
+        r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + mlen; return 2;
+    }
+    __syncwarp(gmask);                                         // earlier stores of this group -> visible
+    copy_match<G>(dst + op, dist, (uint32_t)mlen, sub, gmask);
+    op += (uint32_t)mlen;
+    if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return 2; }                       // :439-443
+    ip_io = ip; op_io = op;
+    return 0;
+}
+
+// Decodes one block with G lanes.  The token chain is walked kSeqBatch sequences ahead; the byte
+// copies of those sequences are then issued together: all literal runs and every match whose source
+// lies entirely before the batch (the common case: SURVEY.md §7.2, DESIGN.md "K2") are loaded
+// back-to-back and stored afterwards, so one L2/HBM round trip serves the whole batch instead of one
+// per sequence.  Matches that read bytes produced inside the batch, overlapping matches and long
+// matches run afterwards, in stream order.
+constexpr int kSeqBatch = 4;
+
+template <int G>
+__device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
+                                                  uint32_t cap, uint32_t sub, uint32_t gmask)
+{
+    constexpr int K = kSeqBatch;
+    constexpr int LJ = (14 + G - 1) / G;          // byte steps for a literal run of at most 14
+    constexpr int MJ = 4;                         // byte steps for a "short" match (<= 4*G bytes)
     DecResult r{0u, LZ4B200_OK, 0ull};
     if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // decompress.rs:207-209
     const WordView view(src);
     uint32_t ip = 0, op = 0;
 
     for (;;) {
-        // ---- token -----------------------------------------------------------------------
-        // One 4-byte fetch covers token + offset + first length byte of a literal-free sequence.
-        const bool wide = ip + 8 <= n;
-        const uint32_t v0 = wide ? view.ro4(ip) : (uint32_t)__ldg(src + ip);
-        const uint32_t tok = v0 & 0xffu;
-        ip++;
-        uint32_t lit = tok >> 4;
-        if (lit == 15) {                                       // read_integer_ptr: decompress.rs:126-157
-            uint64_t acc = 15;
-            for (;;) {
-                if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }
-                uint32_t b = __ldg(src + ip++);
-                acc += b;
-                if (b != 255) break;
-            }
-            if (acc > (uint64_t)(n - ip)) { r.status = LZ4B200_DEC_LITERAL_OUT_OF_BOUNDS; return r; }
-            lit = (uint32_t)acc;
-        }
-        if (lit) {
-            if (lit > n - ip) { r.status = LZ4B200_DEC_LITERAL_OUT_OF_BOUNDS; return r; }        // :346
-            if (lit > cap - op) {                                                                  // :349-354
-                r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + lit; return r;
-            }
-            copy_literals(dst + op, src + ip, lit, lane);
-            ip += lit; op += lit;
-        }
-        if (ip >= n) break;                                    // the stream ends after literals: :366
-        if (n - ip < 2) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }               // :373
-
-        // ---- offset + match length -------------------------------------------------------
-        uint32_t dist, ext0 = 0x100;                           // ext0: first extension byte if prefetched
-        if (wide && tok < 16u) {                               // no literals: all inside v0
-            dist = (v0 >> 8) & 0xffffu; ext0 = v0 >> 24;
-        } else if (ip + 8 <= n) {
-            uint32_t v = view.ro4(ip);
-            dist = v & 0xffffu; ext0 = (v >> 16) & 0xffu;
-        } else {
-            dist = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
-        }
-        ip += 2;
-        if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return r; }                           // :161-173
-        uint64_t mlen = 4u + (tok & 15u);
-        if (mlen == 19) {
-            if (ext0 < 255) { mlen += ext0; ip++; }
-            else {
-                for (;;) {
-                    if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }
-                    uint32_t b = __ldg(src + ip++);
-                    mlen += b;
-                    if (b != 255) break;
+        // ---- phase A: walk up to K sequences that need no check beyond what is tested here ------
+        uint32_t s_lsrc[K], s_lit[K], s_dst[K], s_dist[K], s_mlen[K];
+        const uint32_t batch_op = op;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            s_lit[k] = 0; s_mlen[k] = 0; s_dist[k] = 1; s_dst[k] = op; s_lsrc[k] = ip;
+            if (cnt == k && ip + 8 <= n) {
+                const uint32_t v0 = view.ro4(ip);              // token + (if no literals) offset + ext byte
+                const uint32_t lit = (v0 >> 4) & 15u;
+                const uint32_t q = ip + 1 + lit;               // position of the offset
+                if (lit != 15 && q + 8 <= n) {
+                    uint32_t v1 = v0 >> 8;
+                    if (lit) v1 = view.ro4(q);
+                    const uint32_t dist = v1 & 0xffffu;
+                    uint32_t mlen = 4u + (v0 & 15u), adv = 2;
+                    if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
+                    const uint32_t at = op + lit;              // output position of the match
+                    if (mlen != 19 + 255 && lit + mlen <= cap - op && dist != 0 && dist <= at) {
+                        s_lsrc[k] = ip + 1; s_lit[k] = lit; s_dst[k] = at; s_dist[k] = dist; s_mlen[k] = mlen;
+                        ip = q + adv;                          // < n because q + 8 <= n
+                        op = at + mlen;
+                        cnt = k + 1;
+                    }
                 }
             }
         }
-        if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }                  // :399
-        if (mlen > (uint64_t)(cap - op)) {                                                         // :402-406
-            r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + mlen; return r;
+        // ---- phase B: loads.  Slots beyond cnt have lit = mlen = 0 and load nothing. -------------
+        uint8_t lv[K][LJ], mv[K][MJ];
+        bool later[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int j = 0; j < LJ; j++) {
+                const uint32_t i = sub + j * G;
+                lv[k][j] = 0;
+                if (i < s_lit[k]) lv[k][j] = __ldg(src + s_lsrc[k] + i);
+            }
         }
-        __syncwarp();                                          // earlier stores of this warp -> visible
-        copy_match(dst + op, dist, (uint32_t)mlen, lane);
-        op += (uint32_t)mlen;
-        if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }                   // :439-443
+        __syncwarp(gmask);                        // stores of the previous batch -> visible to every lane
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            // independent of this batch: source ends at or before the batch's first output byte
+            const bool indep = s_dst[k] - s_dist[k] + s_mlen[k] <= batch_op;
+            later[k] = s_mlen[k] != 0 && !(indep && s_mlen[k] <= (uint32_t)(MJ * G));
+            const uint8_t *from = dst + s_dst[k] - s_dist[k];
+#pragma unroll
+            for (int j = 0; j < MJ; j++) {
+                const uint32_t i = sub + j * G;
+                mv[k][j] = 0;
+                if (!later[k] && i < s_mlen[k]) mv[k][j] = from[i];
+            }
+        }
+        // ---- phase C: stores --------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            uint8_t *lto = dst + s_dst[k] - s_lit[k];
+#pragma unroll
+            for (int j = 0; j < LJ; j++) {
+                const uint32_t i = sub + j * G;
+                if (i < s_lit[k]) lto[i] = lv[k][j];
+            }
+            uint8_t *mto = dst + s_dst[k];
+#pragma unroll
+            for (int j = 0; j < MJ; j++) {
+                const uint32_t i = sub + j * G;
+                if (!later[k] && i < s_mlen[k]) mto[i] = mv[k][j];
+            }
+        }
+        // ---- phase D: the matches that had to wait, in stream order -----------------------------
+        bool any_later = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) any_later |= later[k];
+        if (any_later) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (later[k]) {
+                    __syncwarp(gmask);
+                    copy_match<G>(dst + s_dst[k], s_dist[k], s_mlen[k], sub, gmask);
+                }
+            }
+        }
+        if (cnt == K) continue;
+        // ---- the sequence that stopped the walk: every check, one at a time ---------------------
+        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
+        if (c == 1) break;
+        if (c == 2) return r;
+    }
+    r.written = op;
+    return r;
+}
+
+// Simple walk: one sequence at a time (fast path + checked path).
+template <int G>
+__device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
+                                                         uint32_t cap, uint32_t sub, uint32_t gmask)
+{
+    DecResult r{0u, LZ4B200_OK, 0ull};
+    if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // decompress.rs:207-209
+    const WordView view(src);
+    uint32_t ip = 0, op = 0;
+    for (;;) {
+        if (ip + 8 <= n) {
+            const uint32_t v0 = view.ro4(ip);                  // token + (if no literals) offset + ext byte
+            const uint32_t lit = (v0 >> 4) & 15u;
+            const uint32_t q = ip + 1 + lit;                   // position of the offset
+            if (lit != 15 && q + 8 <= n) {
+                uint32_t v1 = v0 >> 8;
+                if (lit) v1 = view.ro4(q);
+                const uint32_t dist = v1 & 0xffffu;
+                uint32_t mlen = 4u + (v0 & 15u), adv = 2;
+                if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
+                const uint32_t at = op + lit;
+                if (mlen != 19 + 255 && lit + mlen <= cap - op && dist != 0 && dist <= at) {
+                    if (lit) {
+                        for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
+                    }
+                    __syncwarp(gmask);
+                    copy_match<G>(dst + at, dist, mlen, sub, gmask);
+                    op = at + mlen;
+                    ip = q + adv;                              // < n because q + 8 <= n
+                    continue;
+                }
+            }
+        }
+        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
+        if (c == 1) break;
+        if (c == 2) return r;
     }
     r.written = op;
     return r;
@@ -208,19 +337,36 @@ __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ sr
 
 constexpr int kDecWarpsPerCta = 4;
 
+template <int G, int kBatched>
 __global__ void __launch_bounds__(kDecWarpsPerCta * 32)
 lz4_decompress_blocks(BatchArgs a)
 {
-    const uint32_t total_warps = gridDim.x * kDecWarpsPerCta;
-    for (uint32_t b = next_ticket(a.tickets); b < a.nblocks; b = next_ticket(a.tickets)) {
-        DecResult r = decode_block(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b]);
-        if (lane_id() == 0) {
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane & (G - 1), leader = lane & ~uint32_t(G - 1);
+    const uint32_t gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << leader);
+    const uint32_t total_groups = gridDim.x * kDecWarpsPerCta * (32 / G);
+    for (;;) {
+        uint32_t b = 0;
+        if (sub == 0) b = atomicAdd(&a.tickets[0], 1u);
+        b = __shfl_sync(gmask, b, leader);
+        if (b >= a.nblocks) break;
+        DecResult r = kBatched
+            ? decode_block<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask)
+            : decode_block_simple<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask);
+        if (sub == 0) {
             a.out_len[b] = r.status == LZ4B200_OK ? r.written : 0u;
             a.status[b] = r.status;
             if (a.err_expected) a.err_expected[b] = r.expected;
         }
     }
-    retire_warp(a.tickets, total_warps);
+    if (sub == 0) {
+        __threadfence();
+        if (atomicAdd(&a.tickets[1], 1u) == total_groups - 1) {
+            a.tickets[0] = 0;
+            a.tickets[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // =============================================================================================

@@ -1,0 +1,160 @@
+"""GPU parity tests of the frame path (independent blocks): FrameEncoder/FrameDecoder mirrors and the one-shot
+C-ABI calls against the oracle's frame encoder — whole frames byte-identical."""
+import io
+
+import numpy as np
+import pytest
+
+import oracle
+from lz4_flex_b200 import corpus, errors, frame
+from lz4_flex_b200.frame import BlockMode, BlockSize, FrameDecoder, FrameEncoder, FrameInfo
+
+pytestmark = pytest.mark.gpu
+
+
+def _flags(info: FrameInfo) -> int:
+    return (oracle.F_BLOCK_CHECKSUMS if info.block_checksums else 0) | \
+           (oracle.F_CONTENT_CHECKSUM if info.content_checksum else 0) | \
+           (oracle.F_CONTENT_SIZE if info.content_size is not None else 0)
+
+
+@pytest.mark.parametrize("bs", [BlockSize.Auto, BlockSize.Max64KB, BlockSize.Max256KB, BlockSize.Max1MB, BlockSize.Max4MB])
+@pytest.mark.parametrize("checks", [False, True])
+def test_one_shot_frames_byte_identical(ctx, bs, checks):
+    for data in (b"", b"a", corpus.load("compression_1k.txt"), corpus.load("compression_66k_JSON.txt"),
+                 corpus.tiled("compression_66k_JSON.txt", 5 * 65536 + 777).tobytes(),
+                 corpus.load("dickens.txt")[: (9 << 20) + 5], bytes(300000),
+                 corpus.adversarial_blocks(6, 0.5).tobytes()):
+        info = FrameInfo(block_size=bs, block_checksums=checks, content_checksum=checks,
+                         content_size=len(data) if checks else None)
+        f = frame.compress_frame(data, info, ctx)
+        assert f == oracle.frame_compress(data, int(bs), _flags(info)), (bs, checks, len(data))
+        assert frame.decompress_frame(f, ctx) == data
+        assert oracle.frame_decompress(f, len(data) + 1)[:2] == (0, data)
+
+
+def test_frame_encoder_write_patterns(ctx):
+    """io::Write behaviour: chunked writes, flush() producing short blocks (stream-offset phase shift),
+    multi-frame reuse, empty input."""
+    data = corpus.tiled("compression_66k_JSON.txt", 700000).tobytes()
+    # one write_all
+    w = io.BytesIO()
+    FrameEncoder(w, FrameInfo(block_size=BlockSize.Max64KB), ctx).write(data)
+    # not finished: last block still buffered
+    enc = FrameEncoder(io.BytesIO(), FrameInfo(block_size=BlockSize.Max64KB), ctx)
+    for i in range(0, len(data), 1000):
+        enc.write(data[i:i + 1000])
+    assert enc.finish().getvalue() == oracle.frame_compress(data, 4)
+    # Auto block size from the first write (header.rs:57-67)
+    enc = FrameEncoder(io.BytesIO(), None, ctx)
+    enc.write(data[:70000]); enc.write(data[70000:])
+    assert enc.frame_info().block_size == BlockSize.Max256KB
+    got = enc.finish().getvalue()
+    assert got[:7] == bytes([4, 0x22, 0x4D, 0x18, 0x60, 0x50, 0xFB])
+    assert frame.decompress_frame(got, ctx) == data
+    # flush every 100 000 bytes
+    enc = FrameEncoder(io.BytesIO(), FrameInfo(block_size=BlockSize.Max64KB), ctx)
+    for i in range(0, len(data), 100000):
+        enc.write(data[i:i + 100000]); enc.flush()
+    assert enc.finish().getvalue() == oracle.frame_compress(data, 4, 0, 100000)
+    # empty input (compress.rs:176-181)
+    assert FrameEncoder(io.BytesIO(), None, ctx).finish().getvalue() == oracle.frame_compress(b"")
+    # auto_finish + second frame from the same encoder
+    sink = io.BytesIO()
+    enc = FrameEncoder(sink, FrameInfo(block_size=BlockSize.Max64KB), ctx)
+    enc.write(data[:200000]); enc.try_finish()
+    enc.write(data[200000:]); enc.try_finish()
+    assert sink.getvalue() == oracle.frame_compress(data[:200000], 4) + oracle.frame_compress(data[200000:], 4)
+    assert FrameDecoder(io.BytesIO(sink.getvalue()), ctx).read() == data      # concatenated (tests.rs:633-647)
+    with FrameEncoder(io.BytesIO(), FrameInfo(block_size=BlockSize.Max64KB), ctx).auto_finish() as af:
+        af.write(data[:5000])
+        inner = af.encoder.get_ref()
+    assert inner.getvalue() == oracle.frame_compress(data[:5000], 4)
+
+
+def test_frame_decoder_reads_and_errors(ctx):
+    a = corpus.load("compression_34k.txt")
+    f = oracle.frame_compress(a, 4, 7)
+    dec = FrameDecoder(io.BytesIO(f), ctx)
+    parts = []
+    while True:
+        p = dec.read(5000)
+        if not p:
+            break
+        parts.append(p)
+    assert b"".join(parts) == a
+    # checksum corruption (tests.rs:650-700)
+    bad = bytearray(oracle.frame_compress(a, 4, oracle.F_BLOCK_CHECKSUMS)); bad[30] ^= 1
+    with pytest.raises(errors.BlockChecksumError):
+        FrameDecoder(io.BytesIO(bytes(bad)), ctx).read()
+    bad = bytearray(oracle.frame_compress(a, 4, oracle.F_CONTENT_CHECKSUM)); bad[-1] ^= 1
+    with pytest.raises(errors.ContentChecksumError):
+        FrameDecoder(io.BytesIO(bytes(bad)), ctx).read()
+    # content size mismatch (tests.rs:721-734)
+    k = corpus.load("compression_1k.txt")
+    with pytest.raises(errors.ContentLengthError) as e:
+        enc = FrameEncoder(io.BytesIO(), FrameInfo(content_size=3), ctx); enc.write(k); enc.finish()
+    assert (e.value.expected, e.value.actual) == (3, 725)
+    # header problems
+    with pytest.raises(errors.WrongMagicNumber):
+        frame.decompress_frame(b"\x00\x01\x02\x03\x04\x05\x06\x07", ctx)
+    with pytest.raises(errors.HeaderChecksumError):
+        frame.decompress_frame(bytes([4, 0x22, 0x4D, 0x18, 0x60, 0x40, 0x83]) + b"\0\0\0\0", ctx)
+    with pytest.raises(errors.SkippableFrame):
+        frame.decompress_frame(bytes([0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, 1, 2, 3, 4]), ctx)
+    with pytest.raises(errors.LinkedBlocksUnsupported):
+        frame.compress_frame(b"abc", FrameInfo(block_mode=BlockMode.Linked), ctx)
+    # corrupt block inside a frame: data before it is still delivered, then DecompressionError
+    d = corpus.tiled("compression_66k_JSON.txt", 3 * 65536).tobytes()
+    g = bytearray(oracle.frame_compress(d, 4))
+    first = int.from_bytes(g[7:11], "little")
+    second_payload = 7 + 4 + first + 4
+    g[second_payload + 3] = 0; g[second_payload + 4] = 0      # poke an offset to zero somewhere early
+    out, err = frame.decompress_frame(bytes(g), ctx, partial=True)
+    es, eo, eb = oracle.frame_decompress(bytes(g), len(d))
+    if es == 0:
+        assert err is None and out == eo
+    else:
+        assert isinstance(err, errors.DecompressionError) and out[:65536] == d[:65536]
+
+
+def test_legacy_frame_fixture(ctx):
+    # tests/tests.rs:741-745 — two 8 MiB-class blocks produced by the C lz4 CLI
+    assert frame.decompress_frame(corpus.load("dickens.lz4"), ctx) == corpus.load("dickens.txt")
+
+
+def test_stored_blocks(ctx):
+    """Incompressible blocks are stored raw (frame/compress.rs:301-306) and decoded from the raw copy."""
+    rnd = corpus.xorshift64star_bytes(3 * 65536 + 100).tobytes()
+    f = frame.compress_frame(rnd, FrameInfo(block_size=BlockSize.Max64KB), ctx)
+    assert f == oracle.frame_compress(rnd, 4)
+    assert int.from_bytes(f[7:11], "little") == (65536 | 0x80000000)
+    assert frame.decompress_frame(f, ctx) == rnd
+
+
+def test_config4_reduced_epochs(ctx):
+    """BASELINE config 4 at reduced size: hdfs log data, 4 MiB blocks, frame format — 24 blocks (96 MiB) via
+    the device block-range entry point, split into two 'ranks' whose outputs concatenate to the oracle frame."""
+    import ctypes as C
+    import torch
+    from lz4_flex_b200 import _native
+    bs, nblk = 4 << 20, 24
+    data = corpus.tiled("hdfs.json", nblk * bs)
+    L = _native.lib()
+    dev = torch.device("cuda", 0)
+    parts = []
+    for r in range(2):
+        lo, hi = r * nblk // 2, (r + 1) * nblk // 2
+        d_in = torch.from_numpy(data[lo * bs: hi * bs]).to(dev)
+        bound = L.lz4b200_frame_blocks_bound(d_in.numel(), bs)
+        d_out = torch.zeros(bound, dtype=torch.uint8, device=dev)
+        d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        st = L.lz4b200_frame_compress_blocks_device(ctx.handle, d_in.data_ptr(), d_in.numel(), bs, lo, d_out.data_ptr(),
+                                                    bound, d_total.data_ptr(), None,
+                                                    torch.cuda.current_stream().cuda_stream)
+        assert st == 0
+        torch.cuda.synchronize()
+        parts.append(d_out[: int(d_total.item())].cpu().numpy().tobytes())
+    got = FrameInfo(block_size=BlockSize.Max4MB).header_bytes() + b"".join(parts) + b"\0\0\0\0"
+    assert got == oracle.frame_compress(data, 7)
+    assert frame.decompress_frame(got, ctx) == data.tobytes()
