@@ -13,7 +13,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
-SO_PATH = os.path.join(_PKG, "liblz4b200.so")
+SO_PATH = os.environ.get("LZ4B200_SO_OVERRIDE") or os.path.join(_PKG, "liblz4b200.so")   # override: tuning builds only
 HEADER = os.path.join(os.path.dirname(_PKG), "include", "lz4b200.h")
 
 NVCC_FLAGS = [
@@ -36,6 +36,8 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> lz4_flex_b200/liblz4b200.so"""
+    if os.environ.get("LZ4B200_SO_OVERRIDE"):
+        return SO_PATH
     if not force and not _stale():
         return SO_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -248,6 +248,7 @@ struct lz4b200_ctx {
     cudaStream_t stream = nullptr;
     uint32_t *d_tickets = nullptr;            // 3 x {next, retired}
     int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
+    int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
     int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
     int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
     int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32 (tuning aid)
@@ -301,9 +302,8 @@ int pick_dec_group(const lz4b200_ctx *ctx, uint32_t nblocks)
 {
     if (ctx->dec_group_override) return ctx->dec_group_override;
     const uint32_t warps = (uint32_t)(ctx->sm_count * ctx->dec_ctas_per_sm * kDecWarpsPerCta);
-    if (nblocks >= warps * 2) return 8;
-    if (nblocks >= warps) return 16;
-    return 32;
+    (void)warps;
+    return nblocks >= 8192 ? 16 : 32;
 }
 
 lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s)
@@ -319,22 +319,46 @@ lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaSt
     }
 }
 
+template <int G>
+lz4b200_status launch_compress16_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStream_t s)
+{
+    constexpr int kWarps = G / 8;                               // 32 KiB of tables per CTA whatever G is
+    constexpr uint32_t per_cta = kWarps * (32 / G);
+    const size_t smem = (size_t)per_cta * 4096 * sizeof(uint16_t);
+    const uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
+    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * 7));
+    lz4_compress_blocks<uint16_t, G, kWarps><<<grid, kWarps * 32, smem, s>>>(a, ctx->d_tickets + 2);
+    CTX_CUDA(ctx, cudaGetLastError());
+    return LZ4B200_OK;
+}
+
+int pick_enc_group(const lz4b200_ctx *ctx, uint32_t nblocks)
+{
+    if (ctx->enc_group_override) return ctx->enc_group_override;
+    const uint32_t tables = (uint32_t)ctx->sm_count * 28;       // 8 KiB tables resident per GPU
+    if (nblocks >= tables) return 8;
+    if (nblocks * 2 >= tables) return 16;
+    return 32;
+}
+
 lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
     {
-        uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
-        uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16_ctas_per_sm));
-        lz4_compress_blocks<uint16_t, kEnc16Warps>
-            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, ctx->d_tickets + 2);
-        CTX_CUDA(ctx, cudaGetLastError());
+        lz4b200_status st;
+        switch (pick_enc_group(ctx, a.nblocks)) {
+        case 8: st = launch_compress16_g<8>(ctx, a, s); break;
+        case 16: st = launch_compress16_g<16>(ctx, a, s); break;
+        default: st = launch_compress16_g<32>(ctx, a, s); break;
+        }
+        if (st != LZ4B200_OK) return st;
     }
     if (max_in_len == 0 || max_in_len > 65536u) {
         uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
-        lz4_compress_blocks<uint32_t, kEnc32Warps>
+        lz4_compress_blocks<uint32_t, 32, kEnc32Warps>
             <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, ctx->d_tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
     }
@@ -398,16 +422,20 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0>,
                                                                       kDecWarpsPerCta * 32, 0), "occupancy dec") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
-                            kEnc16Warps * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
+                            &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, 32, 4>, 128,
+                            4 * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
+                            &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, 32, kEnc32Warps>, kEnc32Warps * 32,
                             kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32");
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
         fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
         lz4b200_ctx_destroy(ctx);
         return LZ4B200_CUDA_ERROR;
+    }
+    if (const char *g = getenv("LZ4B200_ENC_GROUP")) {
+        int v = atoi(g);
+        if (v == 8 || v == 16 || v == 32) ctx->enc_group_override = v;
     }
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);

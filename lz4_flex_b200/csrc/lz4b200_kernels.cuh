@@ -7,6 +7,12 @@
 // counter, one LZ4 block per warp at a time.  This is HBM/L2-bound byte shuffling — no tensor
 // cores.  See DESIGN.md for the layout, the per-kernel roofline and what each phase costs.
 #pragma once
+#ifndef DEC_VARIANT_A
+#define DEC_VARIANT_A 1
+#endif
+#ifndef DEC_COPY_UNROLL
+#define DEC_COPY_UNROLL 1
+#endif
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -111,7 +117,16 @@ __device__ __forceinline__ void copy_match(uint8_t *dst, uint32_t dist, uint32_t
 {
     const uint8_t *from = dst - dist;
     if (dist >= len) {                       // source entirely older than this match
+#if DEC_COPY_UNROLL
+        uint32_t i = sub;
+        for (; i + 3 * G < len; i += 4 * G) {
+            uint8_t a = from[i], b = from[i + G], c = from[i + 2 * G], d = from[i + 3 * G];
+            dst[i] = a; dst[i + G] = b; dst[i + 2 * G] = c; dst[i + 3 * G] = d;
+        }
+        for (; i < len; i += G) dst[i] = from[i];
+#else
         for (uint32_t i = sub; i < len; i += G) dst[i] = from[i];
+#endif
     } else if (dist >= (uint32_t)G) {        // each G-byte step only needs earlier steps
         for (uint32_t base = 0; base < len; base += G) {
             uint32_t i = base + sub;
@@ -314,6 +329,21 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                 const uint32_t dist = v1 & 0xffffu;
                 uint32_t mlen = 4u + (v0 & 15u), adv = 2;
                 if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
+#if DEC_VARIANT_A
+                if ((mlen != 19 + 255) && lit + mlen <= cap - op) {
+                    if (lit) {
+                        for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
+                        op += lit;
+                    }
+                    if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return r; }
+                    if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }
+                    __syncwarp(gmask);
+                    copy_match<G>(dst + op, dist, mlen, sub, gmask);
+                    op += mlen;
+                    ip = q + adv;                              // < n because q + 8 <= n
+                    continue;
+                }
+#else
                 const uint32_t at = op + lit;
                 if (mlen != 19 + 255 && lit + mlen <= cap - op && dist != 0 && dist <= at) {
                     if (lit) {
@@ -325,6 +355,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                     ip = q + adv;                              // < n because q + 8 <= n
                     continue;
                 }
+#endif
             }
         }
         const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
@@ -396,133 +427,177 @@ __device__ __forceinline__ uint32_t slot_h5(uint32_t lo, uint32_t hi8)   // hash
 }
 
 // length-extension bytes for value v (= len - 15) at dst; returns number of bytes written.
-__device__ __forceinline__ uint32_t put_ext(uint8_t *dst, uint32_t v, uint32_t lane)
+template <int G>
+__device__ __forceinline__ uint32_t put_ext(uint8_t *dst, uint32_t v, uint32_t sub)
 {
     uint32_t k = v / 255u, rem = v - k * 255u;
-    for (uint32_t i = lane; i < k; i += 32) dst[i] = 0xff;
-    if (lane == 0) dst[k] = (uint8_t)rem;
+    for (uint32_t i = sub; i < k; i += G) dst[i] = 0xff;
+    if (sub == 0) dst[k] = (uint8_t)rem;
     return k + 1;
 }
 
+template <int G>
 __device__ __forceinline__ uint32_t put_last_literals(uint8_t *dst, const uint8_t *__restrict__ src,
-                                                      uint32_t from, uint32_t n, uint32_t lane)
+                                                      uint32_t from, uint32_t n, uint32_t sub)
 {
     uint32_t len = n - from, o = 1;
-    if (lane == 0) dst[0] = (uint8_t)((len < 15 ? len : 15) << 4);
-    if (len >= 15) o += put_ext(dst + o, len - 15, lane);
-    for (uint32_t i = lane; i < len; i += 32) dst[o + i] = __ldg(src + from + i);
+    if (sub == 0) dst[0] = (uint8_t)((len < 15 ? len : 15) << 4);
+    if (len >= 15) o += put_ext<G>(dst + o, len - 15, sub);
+    for (uint32_t i = sub; i < len; i += G) dst[o + i] = __ldg(src + from + i);
     return o + len;
 }
 
-template <typename TabT>
+// Encodes one block with a group of G lanes (lanes [leader, leader+G) of the warp, mask gmask).
+//
+// Probe batches: the next G probe positions of the reference's probe loop are evaluated at once.
+// The sequential loop reads T[h] and immediately overwrites it with the probe position, so a probe
+// can see the write of an earlier probe of the same batch when their hashes collide.  Fast path: all
+// lanes read their slot, write their position and read the slot back — if every lane reads back its
+// own position, all G hashes were distinct, the first reads are exactly what the sequential loop
+// would have seen, and lanes past the winning probe put the old value back.  Otherwise (hash
+// collision inside the batch, e.g. runs of equal bytes) everything is put back and the exact
+// forwarding path with match.any runs.  Either way the table after the batch equals the reference's.
+template <typename TabT, int G>
 __device__ __forceinline__ uint32_t encode_block(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                              TabT *tab, bool cont, bool h5)
+                                                 TabT *tab, bool cont, bool h5, uint32_t sub, uint32_t leader,
+                                                 uint32_t gmask)
 {
     constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
-    const uint32_t lane = lane_id();
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t lane = leader + sub;
+    const uint32_t lt_mask = gmask & ((1u << lane) - 1u);
     uint32_t o = 0;                                             // output cursor
-    if (n < 13) return put_last_literals(dst, src, 0, n, lane);  // compress.rs:343-346
+    if (n < 13) return put_last_literals<G>(dst, src, 0, n, sub);   // compress.rs:343-346
 
     // table: zero for a fresh table (0 is a legal candidate: position 0), "invalid" when the
     // block continues a frame stream (entries of earlier blocks can never match).
     {
-        constexpr uint32_t words = 4096 * sizeof(TabT) / 4;
-        uint32_t fill = cont ? 0xffffffffu : 0u;
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
-        for (uint32_t i = lane; i < words; i += 32) t32[i] = fill;
-        __syncwarp();
+        constexpr uint32_t words = 4096 * sizeof(TabT) / 16;
+        const uint32_t f = cont ? 0xffffffffu : 0u;
+        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
+        for (uint32_t i = sub; i < words; i += G) t128[i] = make_uint4(f, f, f, f);
+        __syncwarp(gmask);
     }
     const WordView view(src);
     const uint32_t last_probe = n - 12;
+    const uint32_t lim = n - 6;                                 // matches end before the last END_OFFSET bytes
     uint32_t anchor = 0, cur = 0;
     if (!cont) {                                                // compress.rs:353-359
         uint32_t lo, hi; view.ro5(0, lo, hi);
         uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) tab[s] = 0;
+        if (sub == 0) tab[s] = 0;
         cur = 1;
-        __syncwarp();
+        __syncwarp(gmask);
     }
 
     for (;;) {
         // ---- probe batches ----------------------------------------------------------------
-        uint32_t base = cur, stride = 1, cand = 0;
+        uint32_t base = cur, probe0 = 0, cand = 0;
         for (;;) {
-            uint32_t p = base + lane * stride;
-            bool term = p > last_probe;
-            uint32_t key = 0x10000u | lane, v4 = 0, cnd = kInvalid;
+            const uint32_t stride = (probe0 >> 5) + 1u;         // step = (32 + k) >> 5 for probe k
+            const uint32_t p = base + sub * stride;
+            const bool term = p > last_probe;
+            uint32_t key = 0, v4 = 0, old = kInvalid, cv = 0;
+            bool spec = false;
             if (!term) {
                 uint32_t hi; view.ro5(p, v4, hi);
                 key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
-                cnd = tab[key];
+                old = tab[key];
+                spec = old != kInvalid && p - old <= 65535u;
+                if (spec) cv = view.ro4(old);                   // candidate bytes, assuming no in-batch forwarding
+                tab[key] = (TabT)p;
             }
-            uint32_t same = __match_any_sync(kFull, key);
-            uint32_t prior = same & lt_mask;
-            if (prior) cnd = base + (31u - __clz(prior)) * stride;   // forwarded in-batch write
-            bool hit = false;
-            if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
-            uint32_t hits = __ballot_sync(kFull, hit), terms = __ballot_sync(kFull, term);
-            uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
-            uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
-            if (tfirst < win)                                       // compress.rs:381-384
-                return o + put_last_literals(dst + o, src, anchor, n, lane);
-            // commit the table writes of probes 0..win (last writer per slot wins)
-            uint32_t upto = win < 32 ? win : 31u;
-            uint32_t le_mask = upto == 31 ? kFull : ((2u << upto) - 1u);
-            uint32_t mine = same & le_mask;
-            if (lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
-            __syncwarp();
-            if (win < 32) {
-                cur = __shfl_sync(kFull, p, win);
-                cand = __shfl_sync(kFull, cnd, win);
+            __syncwarp(gmask);
+            const bool lost = !term && tab[key] != (TabT)p;     // somebody else wrote my slot
+            const uint32_t terms = __ballot_sync(gmask, term);
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
+            uint32_t win, cnd = old;
+            if (__ballot_sync(gmask, lost) == 0) {
+                const uint32_t hits = __ballot_sync(gmask, spec && cv == v4);
+                win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+                if (tfirst < win)                                   // compress.rs:381-384
+                    return o + put_last_literals<G>(dst + o, src, anchor, n, sub);
+                if (!term && lane > win) tab[key] = (TabT)old;      // probes after the winner never happened
+            } else {
+                // exact path: put everything back, then forward in-batch writes with match.any
+                if (!term) tab[key] = (TabT)old;
+                __syncwarp(gmask);
+                const uint32_t same = __match_any_sync(gmask, term ? (0x10000u | lane) : key);
+                const uint32_t prior = same & lt_mask;
+                if (prior) cnd = base + ((31u - __clz(prior)) - leader) * stride;
+                bool hit = false;
+                if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
+                const uint32_t hits = __ballot_sync(gmask, hit);
+                win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+                if (tfirst < win)
+                    return o + put_last_literals<G>(dst + o, src, anchor, n, sub);
+                // commit the writes of probes up to the winner (last writer per slot wins)
+                const uint32_t le_mask = win >= 31u ? kFull : ((2u << win) - 1u);
+                const uint32_t mine = same & le_mask;
+                if (!term && lane <= win && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
+            }
+            __syncwarp(gmask);
+            if (win < 32u) {
+                cur = __shfl_sync(gmask, p, win);
+                cand = __shfl_sync(gmask, cnd, win);
                 break;
             }
-            base += 32u * stride;
-            stride++;
+            base += (uint32_t)G * stride;
+            probe0 += G;
         }
         const uint32_t dist = cur - cand;
 
-        // ---- extend backwards (compress.rs:272-287) ---------------------------------------
-        for (;;) {
-            uint32_t room = min(cand, cur - anchor);                // how far both may step back
-            bool ok = lane < room && __ldg(src + cur - 1 - lane) == __ldg(src + cand - 1 - lane);
-            uint32_t bad = ~__ballot_sync(kFull, ok);
-            uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+        // ---- extend.  The first forward window (4 bytes per lane from cur+4 / cand+4) is loaded before the
+        //      backward loop so both directions share one memory round trip.
+        uint32_t fbase = cur + 4;                                   // forward cursor (input side); match side = -dist
+        uint32_t fx = 1;                                            // xor of the two sides, nonzero = mismatch
+        bool ffull = fbase + 4 * sub + 4 <= lim;                    // this lane's word lies before n - END_OFFSET
+        if (ffull) fx = view.ro4(fbase + 4 * sub) ^ view.ro4(fbase + 4 * sub - dist);
+        for (;;) {                                                  // backward: compress.rs:272-287
+            const uint32_t room = min(cand, cur - anchor);          // how far both may step back
+            const bool ok = sub < room && __ldg(src + cur - 1 - sub) == __ldg(src + cand - 1 - sub);
+            const uint32_t bad = gmask & ~__ballot_sync(gmask, ok);
+            const uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u - leader : (uint32_t)G;
             cur -= k; cand -= k;
-            if (k < 32) break;
+            if (k < (uint32_t)G) break;
         }
         const uint32_t lit = cur - anchor;
-
-        // ---- extend forwards (compress.rs:156-216), limit n - 6 ---------------------------
-        cur += 4; cand += 4;
-        uint32_t extra = 0;
-        {
-            const uint32_t lim = n - 6;
-            for (;;) {
-                uint32_t q = cur + lane;
-                bool ok = q < lim && __ldg(src + q) == __ldg(src + cand + lane);
-                uint32_t bad = ~__ballot_sync(kFull, ok);
-                uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
-                extra += k; cur += k; cand += k;
-                if (k < 32) break;
+        for (;;) {                                                  // forward: compress.rs:156-216
+            const uint32_t nm = ffull ? (fx ? (uint32_t)(__ffs(fx) - 1) >> 3 : 4u) : 0u;
+            const uint32_t bad = __ballot_sync(gmask, nm < 4u);
+            if (bad) {
+                const uint32_t fl = (uint32_t)__ffs(bad) - 1u;       // first lane whose word stops the match
+                fbase += 4u * (fl - leader) + __shfl_sync(gmask, nm, fl);
+                break;
             }
+            fbase += 4u * G;
+            ffull = fbase + 4 * sub + 4 <= lim;
+            fx = 1;
+            if (ffull) fx = view.ro4(fbase + 4 * sub) ^ view.ro4(fbase + 4 * sub - dist);
         }
+        if (fbase < lim) {                                          // a word that crossed n - 6: finish bytewise
+            const uint32_t q = fbase + sub;
+            const bool ok = sub < 4u && q < lim && __ldg(src + q) == __ldg(src + q - dist);
+            const uint32_t bad = gmask & ~__ballot_sync(gmask, ok);
+            fbase += (uint32_t)__ffs(bad) - 1u - leader;            // lanes >= 4 always stop: at most 3 more bytes
+        }
+        const uint32_t extra = fbase - (cur + 4);                   // duplicate_length: match bytes beyond MINMATCH
+        cur = fbase;
         // ---- T[H(cur-2)] = cur-2 (compress.rs:460-461) ------------------------------------
         {
             uint32_t lo, hi; view.ro5(cur - 2, lo, hi);
             uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-            if (lane == 0) tab[s] = (TabT)(cur - 2);
-            __syncwarp();
+            if (sub == 0) tab[s] = (TabT)(cur - 2);
+            __syncwarp(gmask);
         }
         // ---- emit the sequence (compress.rs:463-486) --------------------------------------
-        if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
+        if (sub == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
         o++;
-        if (lit >= 15) o += put_ext(dst + o, lit - 15, lane);
-        for (uint32_t i = lane; i < lit; i += 32) dst[o + i] = __ldg(src + anchor + i);
+        if (lit >= 15) o += put_ext<G>(dst + o, lit - 15, sub);
+        for (uint32_t i = sub; i < lit; i += G) dst[o + i] = __ldg(src + anchor + i);
         o += lit;
-        if (lane == 0) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }
+        if (sub == 0) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }
         o += 2;
-        if (extra >= 15) o += put_ext(dst + o, extra - 15, lane);
+        if (extra >= 15) o += put_ext<G>(dst + o, extra - 15, sub);
         anchor = cur;
     }
 }
@@ -532,19 +607,26 @@ __device__ __forceinline__ uint64_t max_output_size_dev(uint32_t n)
     return 20ull + ((uint64_t)n * 110ull) / 100ull;
 }
 
-// One CTA = kWarps warps, each with a private 4096-slot table in shared memory.
-// Blocks of up to 65 536 bytes use the TabT=uint16_t instantiation (8 KiB per warp), larger
-// ones uint32_t (16 KiB per warp); the host launches both over the same ticket space and each
-// instantiation skips the blocks that belong to the other.
-template <typename TabT, int kWarps>
+// One CTA = kWarps warps; every group of G lanes owns a private 4096-slot table in shared memory
+// (32/G tables per warp).  Blocks of up to 65 536 bytes use the TabT=uint16_t instantiation (8 KiB
+// per table), larger ones uint32_t (16 KiB); the host launches both over the same ticket space and
+// each instantiation skips the blocks that belong to the other.
+template <typename TabT, int G, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32)
 lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    TabT *tab = reinterpret_cast<TabT *>(smem_raw) + (threadIdx.x >> 5) * 4096;
-    const uint32_t total_warps = gridDim.x * kWarps;
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane & (G - 1), leader = lane & ~uint32_t(G - 1);
+    const uint32_t gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << leader);
+    TabT *tab = reinterpret_cast<TabT *>(smem_raw) + ((threadIdx.x >> 5) * (32 / G) + leader / G) * 4096;
+    const uint32_t total_groups = gridDim.x * kWarps * (32 / G);
     constexpr bool kSmall = sizeof(TabT) == 2;
-    for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
+    for (;;) {
+        uint32_t b = 0;
+        if (sub == 0) b = atomicAdd(&tickets[0], 1u);
+        b = __shfl_sync(gmask, b, leader);
+        if (b >= a.nblocks) break;
         const uint32_t n = a.in_len[b];
         if ((n <= 65536u) != kSmall) continue;
         const uint32_t fl = a.flags ? a.flags[b] : 0u;
@@ -553,12 +635,19 @@ lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
             st = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
         } else {
             const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;   // compress.rs:559
-            written = encode_block<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
-                                         (fl & LZ4B200_BLOCK_CONT) != 0, h5);
+            written = encode_block<TabT, G>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
+                                            (fl & LZ4B200_BLOCK_CONT) != 0, h5, sub, leader, gmask);
         }
-        if (lane_id() == 0) { a.out_len[b] = written; a.status[b] = st; }
+        if (sub == 0) { a.out_len[b] = written; a.status[b] = st; }
     }
-    retire_warp(tickets, total_warps);
+    if (sub == 0) {
+        __threadfence();
+        if (atomicAdd(&tickets[1], 1u) == total_groups - 1) {
+            tickets[0] = 0;
+            tickets[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace lz4b200
