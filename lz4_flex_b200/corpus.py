@@ -62,8 +62,9 @@ def xorshift64star_bytes(nbytes: int, seed: int = 0x9E3779B97F4A7C15) -> np.ndar
 
 def adversarial_blocks(nblocks: int, zero_fraction: float, block: int = 65536) -> np.ndarray:
     """Config 5: `nblocks` blocks, a `zero_fraction` share all-zero (evenly interleaved), the rest
-    incompressible; deterministic."""
-    rnd = xorshift64star_bytes(block * 16)
+    incompressible (distinct windows of one xorshift64* stream); deterministic."""
+    extra = 8 * (nblocks // 16 + 1)
+    rnd = xorshift64star_bytes(block * 16 + extra)
     out = np.zeros(nblocks * block, dtype=np.uint8)
     acc = 0.0
     k = 0
@@ -72,9 +73,7 @@ def adversarial_blocks(nblocks: int, zero_fraction: float, block: int = 65536) -
         if acc >= 1.0 - 1e-9:
             acc -= 1.0
             continue  # zero block
-        # rotate through 16 distinct random blocks, perturbed by the block index
-        chunk = rnd[(k % 16) * block:(k % 16 + 1) * block].copy()
-        chunk[:8] = np.frombuffer(int(b).to_bytes(8, "little"), dtype=np.uint8)
-        out[b * block:(b + 1) * block] = chunk
+        start = (k % 16) * block + (k // 16) * 8
+        out[b * block:(b + 1) * block] = rnd[start:start + block]
         k += 1
     return out

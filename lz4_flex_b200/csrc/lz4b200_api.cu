@@ -270,7 +270,10 @@ struct lz4b200_ctx {
 
 namespace {
 
-constexpr int kEnc16Warps = 4;     // 4 x 8 KiB tables per CTA
+#ifndef ENC16_WARPS
+#define ENC16_WARPS 4
+#endif
+constexpr int kEnc16Warps = ENC16_WARPS;   // 8 KiB table per warp; 1-warp CTAs give the finest smem granularity
 constexpr int kEnc32Warps = 2;     // 2 x 16 KiB tables per CTA
 
 #define CTX_CUDA(ctx, call)                                              \
@@ -319,46 +322,22 @@ lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaSt
     }
 }
 
-template <int G>
-lz4b200_status launch_compress16_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStream_t s)
-{
-    constexpr int kWarps = G / 8;                               // 32 KiB of tables per CTA whatever G is
-    constexpr uint32_t per_cta = kWarps * (32 / G);
-    const size_t smem = (size_t)per_cta * 4096 * sizeof(uint16_t);
-    const uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
-    const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * 7));
-    lz4_compress_blocks<uint16_t, G, kWarps><<<grid, kWarps * 32, smem, s>>>(a, ctx->d_tickets + 2);
-    CTX_CUDA(ctx, cudaGetLastError());
-    return LZ4B200_OK;
-}
-
-int pick_enc_group(const lz4b200_ctx *ctx, uint32_t nblocks)
-{
-    if (ctx->enc_group_override) return ctx->enc_group_override;
-    const uint32_t tables = (uint32_t)ctx->sm_count * 28;       // 8 KiB tables resident per GPU
-    if (nblocks >= tables) return 8;
-    if (nblocks * 2 >= tables) return 16;
-    return 32;
-}
-
 lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
     {
-        lz4b200_status st;
-        switch (pick_enc_group(ctx, a.nblocks)) {
-        case 8: st = launch_compress16_g<8>(ctx, a, s); break;
-        case 16: st = launch_compress16_g<16>(ctx, a, s); break;
-        default: st = launch_compress16_g<32>(ctx, a, s); break;
-        }
-        if (st != LZ4B200_OK) return st;
+        uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
+        uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16_ctas_per_sm));
+        lz4_compress_blocks<uint16_t, kEnc16Warps>
+            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, ctx->d_tickets + 2);
+        CTX_CUDA(ctx, cudaGetLastError());
     }
     if (max_in_len == 0 || max_in_len > 65536u) {
         uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
-        lz4_compress_blocks<uint32_t, 32, kEnc32Warps>
+        lz4_compress_blocks<uint32_t, kEnc32Warps>
             <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, ctx->d_tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
     }
@@ -422,10 +401,10 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0>,
                                                                       kDecWarpsPerCta * 32, 0), "occupancy dec") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, 32, 4>, 128,
-                            4 * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
+                            &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
+                            kEnc16Warps * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, 32, kEnc32Warps>, kEnc32Warps * 32,
+                            &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
                             kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32");
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
