@@ -83,6 +83,9 @@ typedef struct lz4b200_ctx lz4b200_ctx;
 /* ---- library / context --------------------------------------------------------------- */
 
 int lz4b200_abi_version(void);
+/* How this library's CUDA runtime sees a host pointer: 0 pageable, 1 pinned, 2 device, 3 managed, -1 unknown.
+ * The host batch calls overlap PCIe traffic with kernels only for pinned (page-locked) buffers. */
+int lz4b200_host_pointer_kind(const void *p);
 const char *lz4b200_status_string(int status);
 /* Last CUDA error text seen by this context (empty string if none). */
 const char *lz4b200_last_cuda_error(const lz4b200_ctx *ctx);

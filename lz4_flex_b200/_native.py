@@ -68,6 +68,7 @@ _psz = C.POINTER(C.c_size_t)
 # name -> (restype, argtypes).  Kept in one table so tests can check every symbol the header declares.
 SIGNATURES = {
     "lz4b200_abi_version": (_i32, []),
+    "lz4b200_host_pointer_kind": (_i32, [_vp]),
     "lz4b200_status_string": (C.c_char_p, [_i32]),
     "lz4b200_last_cuda_error": (C.c_char_p, [_vp]),
     "lz4b200_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),

@@ -242,7 +242,10 @@ template <typename T> struct DevBuf {
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+static void pipeline_destroy(void *p);
+
 struct lz4b200_ctx {
+    void *pipe = nullptr;                     // host-batch pipeline state (streams, pinned staging), created on demand
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -309,11 +312,11 @@ int pick_dec_group(const lz4b200_ctx *ctx, uint32_t nblocks)
     return nblocks >= 8192 ? 16 : 32;
 }
 
-lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s)
+lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s, uint32_t *tickets = nullptr)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
-    a.tickets = ctx->d_tickets;
+    a.tickets = tickets ? tickets : ctx->d_tickets;
     switch (pick_dec_group(ctx, a.nblocks)) {
     case 4: return launch_decompress_g<4>(ctx, a, s);
     case 8: return launch_decompress_g<8>(ctx, a, s);
@@ -322,8 +325,10 @@ lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaSt
     }
 }
 
-lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s)
+lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s,
+                               uint32_t *tickets = nullptr)
 {
+    if (!tickets) tickets = ctx->d_tickets;
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
@@ -331,14 +336,14 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16_ctas_per_sm));
         lz4_compress_blocks<uint16_t, kEnc16Warps>
-            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, ctx->d_tickets + 2);
+            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, tickets + 2);
         CTX_CUDA(ctx, cudaGetLastError());
     }
     if (max_in_len == 0 || max_in_len > 65536u) {
         uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
         lz4_compress_blocks<uint32_t, kEnc32Warps>
-            <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, ctx->d_tickets + 4);
+            <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
     }
     return LZ4B200_OK;
@@ -349,6 +354,13 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
 extern "C" {
 
 int lz4b200_abi_version(void) { return LZ4B200_ABI_VERSION; }
+
+int lz4b200_host_pointer_kind(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int)a.type;                       // 0 unregistered (pageable), 1 host (pinned), 2 device, 3 managed
+}
 
 const char *lz4b200_status_string(int s)
 {
@@ -432,6 +444,7 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
     DeviceGuard guard(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    pipeline_destroy(ctx->pipe);
     ctx->d_in.release(); ctx->d_out.release(); ctx->d_slots.release(); ctx->d_flags.release(); ctx->d_pick.release();
     ctx->d_in_off.release(); ctx->d_out_off.release(); ctx->d_seg_off.release(); ctx->d_expected.release();
     ctx->d_off_b.release();
@@ -505,6 +518,86 @@ lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *
 }
 
 // ---- host batch entry points --------------------------------------------------------------------
+// Both calls are chunked software pipelines over kLanes streams: while chunk c runs its kernel, chunk
+// c+1's input crosses PCIe host->device and chunk c-1's result crosses device->host (full duplex), so
+// a large batch runs at max(PCIe, kernel) instead of their sum.
+
+}  // extern "C"
+
+namespace {
+
+constexpr int kLanes = 3;
+constexpr uint64_t kChunkBytes = 32ull << 20;            // decompress: PCIe-bound, small chunks pipeline best
+// compress: a 64 KiB block is one ~5 ms serial chain whatever the batch size, so a chunk must hold enough blocks
+// (2048 = 58 % of the resident warps) for two chunks in flight to fill the GPU
+constexpr uint64_t kCompressChunkBytes = 128ull << 20;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t sizes_ready = nullptr;
+    DevBuf<uint8_t> in, slots, out;
+};
+
+struct Pipeline {
+    Lane lane[kLanes];
+    cudaEvent_t desc_ready = nullptr;
+    uint32_t *d_tickets = nullptr;           // kLanes x 8 counters
+    uint64_t *h_seg = nullptr; size_t h_seg_cap = 0;       // pinned
+    int32_t *h_status = nullptr; size_t h_status_cap = 0;  // pinned
+    bool ready = false;
+};
+
+lz4b200_status pipeline_init(lz4b200_ctx *ctx, Pipeline &p)
+{
+    if (p.ready) return LZ4B200_OK;
+    for (int i = 0; i < kLanes; i++) {
+        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p.lane[i].stream, cudaStreamNonBlocking));
+        CTX_CUDA(ctx, cudaEventCreateWithFlags(&p.lane[i].sizes_ready, cudaEventDisableTiming));
+    }
+    CTX_CUDA(ctx, cudaEventCreateWithFlags(&p.desc_ready, cudaEventDisableTiming));
+    CTX_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&p.d_tickets), kLanes * 8 * sizeof(uint32_t)));
+    CTX_CUDA(ctx, cudaMemset(p.d_tickets, 0, kLanes * 8 * sizeof(uint32_t)));
+    p.ready = true;
+    return LZ4B200_OK;
+}
+
+template <typename T> cudaError_t pinned_reserve(T *&ptr, size_t &cap, size_t n)
+{
+    if (n <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; cap = 0;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&ptr), (n + n / 4 + 64) * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = n + n / 4 + 64;
+    return e;
+}
+
+struct Chunk { uint32_t b0, b1; uint64_t in_lo, in_hi, a, b; };   // a/b: slot bytes (compress) or out_lo/out_hi (decompress)
+
+}  // namespace
+
+static Pipeline &ctx_pipeline(lz4b200_ctx *ctx)
+{
+    if (!ctx->pipe) ctx->pipe = new Pipeline();
+    return *static_cast<Pipeline *>(ctx->pipe);
+}
+
+static void pipeline_destroy(void *vp)
+{
+    Pipeline *p = static_cast<Pipeline *>(vp);
+    if (!p) return;
+    for (int i = 0; i < kLanes; i++) {
+        if (p->lane[i].stream) { cudaStreamSynchronize(p->lane[i].stream); cudaStreamDestroy(p->lane[i].stream); }
+        if (p->lane[i].sizes_ready) cudaEventDestroy(p->lane[i].sizes_ready);
+        p->lane[i].in.release(); p->lane[i].slots.release(); p->lane[i].out.release();
+    }
+    if (p->desc_ready) cudaEventDestroy(p->desc_ready);
+    if (p->d_tickets) cudaFree(p->d_tickets);
+    if (p->h_seg) cudaFreeHost(p->h_seg);
+    if (p->h_status) cudaFreeHost(p->h_status);
+    delete p;
+}
+
+extern "C" {
 
 lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
                                            const uint32_t *in_len, const uint8_t *flags, uint8_t *out,
@@ -515,66 +608,111 @@ lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, 
     if (nblocks == 0) return LZ4B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_len || !status) return LZ4B200_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = ctx->stream;
+    Pipeline &pl = ctx_pipeline(ctx);
+    lz4b200_status st = pipeline_init(ctx, pl);
+    if (st != LZ4B200_OK) return st;
     const uint32_t nb = (uint32_t)nblocks;
 
-    // input span and padded device slots
-    uint64_t lo = ~0ull, hi = 0, slot_total = 0;
-    uint32_t max_len = 0;
+    // ---- plan: chunks of ~kChunkBytes input, descriptors relative to each chunk's buffers ------
+    std::vector<Chunk> chunks;
     std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
     std::vector<uint32_t> h_cap(nb);
-    for (uint32_t b = 0; b < nb; b++) {
-        lo = std::min<uint64_t>(lo, in_off[b]);
-        hi = std::max<uint64_t>(hi, in_off[b] + in_len[b]);
-        max_len = std::max(max_len, in_len[b]);
+    uint32_t max_len = 0;
+    for (uint32_t b = 0; b < nb;) {
+        Chunk c{b, b, ~0ull, 0, 0, 0};
+        uint64_t bytes = 0;
+        while (c.b1 < nb && (c.b1 == c.b0 || bytes + in_len[c.b1] <= kCompressChunkBytes)) {
+            const uint32_t k = c.b1++;
+            c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]);
+            c.in_hi = std::max<uint64_t>(c.in_hi, in_off[k] + in_len[k]);
+            bytes += in_len[k];
+            max_len = std::max(max_len, in_len[k]);
+            const size_t m = lz4b200_max_output_size(in_len[k]);
+            if (m > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+            h_cap[k] = (uint32_t)m;
+            h_slot_off[k] = c.a;
+            c.a += (m + 15) & ~size_t(15);
+        }
+        for (uint32_t k = c.b0; k < c.b1; k++) h_in_off[k] = in_off[k] - c.in_lo;
+        chunks.push_back(c);
+        b = c.b1;
     }
-    for (uint32_t b = 0; b < nb; b++) {
-        h_in_off[b] = in_off[b] - lo;
-        h_slot_off[b] = slot_total;
-        size_t m = lz4b200_max_output_size(in_len[b]);
-        if (m > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
-        h_cap[b] = (uint32_t)m;
-        slot_total += (m + 15) & ~size_t(15);
-    }
-    const uint64_t span = hi - lo;
-    CTX_CUDA(ctx, ctx->d_in.reserve(span + 16));
-    CTX_CUDA(ctx, ctx->d_slots.reserve(slot_total + 16));
+    const uint32_t nch = (uint32_t)chunks.size();
     CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
     CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
     CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
-    CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + 1));
+    CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + nch));
     if (flags) CTX_CUDA(ctx, ctx->d_flags.reserve(nb));
+    CTX_CUDA(ctx, pinned_reserve(pl.h_seg, pl.h_seg_cap, (size_t)nb + nch));
+    CTX_CUDA(ctx, pinned_reserve(pl.h_status, pl.h_status_cap, nb));
 
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in + lo, span, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s));
-    if (flags) CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, flags, nb, cudaMemcpyHostToDevice, s));
+    cudaStream_t s0 = pl.lane[0].stream;
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s0));
+    if (flags) CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, flags, nb, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaEventRecord(pl.desc_ready, s0));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s0));            // the host vectors above may go out of scope before use otherwise
 
-    BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, flags ? ctx->d_flags.p : nullptr, ctx->d_slots.p,
-                ctx->d_out_off.p, ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
-    lz4b200_status st = launch_compress(ctx, a, max_len, s);
-    if (st != LZ4B200_OK) return st;
+    auto phase1 = [&](uint32_t ci) -> lz4b200_status {  // H2D + kernel + scan + sizes D2H
+        const Chunk &c = chunks[ci];
+        Lane &ln = pl.lane[ci % kLanes];
+        const uint32_t n = c.b1 - c.b0;
+        CTX_CUDA(ctx, ln.in.reserve(c.in_hi - c.in_lo + 16));
+        CTX_CUDA(ctx, ln.slots.reserve(c.a + 16));
+        CTX_CUDA(ctx, cudaStreamWaitEvent(ln.stream, pl.desc_ready, 0));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ln.in.p, in + c.in_lo, c.in_hi - c.in_lo, cudaMemcpyHostToDevice, ln.stream));
+        BatchArgs a{ln.in.p, ctx->d_in_off.p + c.b0, ctx->d_in_len.p + c.b0, flags ? ctx->d_flags.p + c.b0 : nullptr,
+                    ln.slots.p, ctx->d_out_off.p + c.b0, ctx->d_out_cap.p + c.b0, ctx->d_out_len.p + c.b0,
+                    ctx->d_status.p + c.b0, nullptr, n, nullptr};
+        lz4b200_status r = launch_compress(ctx, a, max_len, ln.stream, pl.d_tickets + 8 * (ci % kLanes));
+        if (r != LZ4B200_OK) return r;
+        scan_sizes_kernel<<<1, 1024, 0, ln.stream>>>(ctx->d_out_len.p + c.b0, ctx->d_seg_off.p + c.b0 + ci, n);
+        CTX_CUDA(ctx, cudaGetLastError());
+        CTX_CUDA(ctx, cudaMemcpyAsync(pl.h_seg + c.b0 + ci, ctx->d_seg_off.p + c.b0 + ci, (n + 1) * 8,
+                                      cudaMemcpyDeviceToHost, ln.stream));
+        CTX_CUDA(ctx, cudaEventRecord(ln.sizes_ready, ln.stream));
+        return LZ4B200_OK;
+    };
 
-    // pack: scan the produced lengths, gather slots -> dense buffer, one D2H of exactly the payload
-    scan_sizes_kernel<<<1, 1024, 0, s>>>(ctx->d_out_len.p, ctx->d_seg_off.p, nb);
-    CTX_CUDA(ctx, cudaGetLastError());
-    CTX_CUDA(ctx, cudaMemcpyAsync(out_len, ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
-    std::vector<uint64_t> h_seg(nb + 1);
-    CTX_CUDA(ctx, cudaMemcpyAsync(h_seg.data(), ctx->d_seg_off.p, (nb + 1) * 8, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(ctx, cudaStreamSynchronize(s));
-    const uint64_t total = h_seg[nb];
-    for (uint32_t b = 0; b < nb; b++) out_off[b] = h_seg[b];
-    if (total > out_cap_total) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
-    CTX_CUDA(ctx, ctx->d_out.reserve(total + 16));
-    GatherArgs g{ctx->d_slots.p, nullptr, ctx->d_out_off.p, nullptr, ctx->d_out_len.p, nullptr, nullptr, nullptr,
-                 ctx->d_out.p, ctx->d_seg_off.p, nb};
-    gather_segments_kernel<<<std::min<uint32_t>(nb, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
-    CTX_CUDA(ctx, cudaGetLastError());
-    CTX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    for (uint32_t ci = 0; ci < nch && ci < (uint32_t)kLanes; ci++) {
+        st = phase1(ci);
+        if (st != LZ4B200_OK) return st;
+    }
+    uint64_t out_base = 0;
+    lz4b200_status result = LZ4B200_OK;
+    for (uint32_t ci = 0; ci < nch; ci++) {
+        const Chunk &c = chunks[ci];
+        Lane &ln = pl.lane[ci % kLanes];
+        const uint32_t n = c.b1 - c.b0;
+        CTX_CUDA(ctx, cudaEventSynchronize(ln.sizes_ready));
+        const uint64_t *seg = pl.h_seg + c.b0 + ci;
+        const uint64_t total = seg[n];
+        for (uint32_t k = 0; k < n; k++) {
+            out_off[c.b0 + k] = out_base + seg[k];
+            out_len[c.b0 + k] = (uint32_t)(seg[k + 1] - seg[k]);
+        }
+        if (out_base + total > out_cap_total) { result = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; break; }
+        if (total) {
+            CTX_CUDA(ctx, ln.out.reserve(total + 16));
+            GatherArgs g{ln.slots.p, nullptr, ctx->d_out_off.p + c.b0, nullptr, ctx->d_out_len.p + c.b0, nullptr, nullptr,
+                         nullptr, ln.out.p, ctx->d_seg_off.p + c.b0 + ci, n};
+            gather_segments_kernel<<<std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 8), 256, 0, ln.stream>>>(g);
+            CTX_CUDA(ctx, cudaGetLastError());
+            CTX_CUDA(ctx, cudaMemcpyAsync(out + out_base, ln.out.p, total, cudaMemcpyDeviceToHost, ln.stream));
+        }
+        out_base += total;
+        if (ci + kLanes < nch) {
+            st = phase1(ci + kLanes);
+            if (st != LZ4B200_OK) return st;
+        }
+    }
+    for (int i = 0; i < kLanes; i++) CTX_CUDA(ctx, cudaStreamSynchronize(pl.lane[i].stream));
+    if (result != LZ4B200_OK) return result;
+    CTX_CUDA(ctx, cudaMemcpyAsync(pl.h_status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s0));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s0));
+    memcpy(status, pl.h_status, nb * 4);
     return LZ4B200_OK;
 }
 
@@ -588,47 +726,77 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in
     if (!in || !in_off || !in_len || !out || !out_off || !out_cap || !out_len || !status)
         return LZ4B200_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = ctx->stream;
+    Pipeline &pl = ctx_pipeline(ctx);
+    lz4b200_status st = pipeline_init(ctx, pl);
+    if (st != LZ4B200_OK) return st;
     const uint32_t nb = (uint32_t)nblocks;
-    uint64_t ilo = ~0ull, ihi = 0, olo = ~0ull, ohi = 0;
-    bool contiguous = true;
-    for (uint32_t b = 0; b < nb; b++) {
-        ilo = std::min<uint64_t>(ilo, in_off[b]); ihi = std::max<uint64_t>(ihi, in_off[b] + in_len[b]);
-        olo = std::min<uint64_t>(olo, out_off[b]); ohi = std::max<uint64_t>(ohi, out_off[b] + out_cap[b]);
-        if (b && out_off[b] != out_off[b - 1] + out_cap[b - 1]) contiguous = false;
-    }
+
+    std::vector<Chunk> chunks;
+    std::vector<uint8_t> contiguous;
     std::vector<uint64_t> h_in_off(nb), h_out_off(nb);
-    for (uint32_t b = 0; b < nb; b++) { h_in_off[b] = in_off[b] - ilo; h_out_off[b] = out_off[b] - olo; }
-    CTX_CUDA(ctx, ctx->d_in.reserve(ihi - ilo + 16));
-    CTX_CUDA(ctx, ctx->d_out.reserve(ohi - olo + 16));
+    for (uint32_t b = 0; b < nb;) {
+        Chunk c{b, b, ~0ull, 0, ~0ull, 0};
+        uint64_t bytes = 0;
+        bool contig = true;
+        while (c.b1 < nb && (c.b1 == c.b0 || bytes + out_cap[c.b1] <= kChunkBytes)) {
+            const uint32_t k = c.b1++;
+            c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]); c.in_hi = std::max<uint64_t>(c.in_hi, in_off[k] + in_len[k]);
+            c.a = std::min<uint64_t>(c.a, out_off[k]); c.b = std::max<uint64_t>(c.b, out_off[k] + out_cap[k]);
+            if (k > c.b0 && out_off[k] != out_off[k - 1] + out_cap[k - 1]) contig = false;
+            bytes += out_cap[k];
+        }
+        for (uint32_t k = c.b0; k < c.b1; k++) { h_in_off[k] = in_off[k] - c.in_lo; h_out_off[k] = out_off[k] - c.a; }
+        chunks.push_back(c);
+        contiguous.push_back(contig ? 1 : 0);
+        b = c.b1;
+    }
+    const uint32_t nch = (uint32_t)chunks.size();
     CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
     CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
     CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
     CTX_CUDA(ctx, ctx->d_expected.reserve(nb));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in + ilo, ihi - ilo, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_out_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, out_cap, nb * 4, cudaMemcpyHostToDevice, s));
-    BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_out.p, ctx->d_out_off.p,
-                ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, ctx->d_expected.p, nb, nullptr};
-    lz4b200_status st = launch_decompress(ctx, a, s);
-    if (st != LZ4B200_OK) return st;
-    CTX_CUDA(ctx, cudaMemcpyAsync(out_len, ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
-    CTX_CUDA(ctx, cudaMemcpyAsync(status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
-    if (err_expected)
-        CTX_CUDA(ctx, cudaMemcpyAsync(err_expected, ctx->d_expected.p, nb * 8, cudaMemcpyDeviceToHost, s));
-    if (contiguous) {
-        CTX_CUDA(ctx, cudaMemcpyAsync(out + olo, ctx->d_out.p, ohi - olo, cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(ctx, cudaStreamSynchronize(s));
-    } else {
-        CTX_CUDA(ctx, cudaStreamSynchronize(s));
-        for (uint32_t b = 0; b < nb; b++)
-            if (out_len[b])
-                CTX_CUDA(ctx, cudaMemcpyAsync(out + out_off[b], ctx->d_out.p + h_out_off[b], out_len[b],
-                                              cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(ctx, cudaStreamSynchronize(s));
+    CTX_CUDA(ctx, pinned_reserve(pl.h_seg, pl.h_seg_cap, (size_t)nb));
+    CTX_CUDA(ctx, pinned_reserve(pl.h_status, pl.h_status_cap, (size_t)nb * 2));
+    cudaStream_t s0 = pl.lane[0].stream;
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_out_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, out_cap, nb * 4, cudaMemcpyHostToDevice, s0));
+    CTX_CUDA(ctx, cudaEventRecord(pl.desc_ready, s0));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s0));
+
+    for (uint32_t ci = 0; ci < nch; ci++) {
+        const Chunk &c = chunks[ci];
+        Lane &ln = pl.lane[ci % kLanes];
+        const uint32_t n = c.b1 - c.b0;
+        CTX_CUDA(ctx, ln.in.reserve(c.in_hi - c.in_lo + 16));
+        CTX_CUDA(ctx, ln.out.reserve(c.b - c.a + 16));
+        CTX_CUDA(ctx, cudaStreamWaitEvent(ln.stream, pl.desc_ready, 0));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ln.in.p, in + c.in_lo, c.in_hi - c.in_lo, cudaMemcpyHostToDevice, ln.stream));
+        BatchArgs a{ln.in.p, ctx->d_in_off.p + c.b0, ctx->d_in_len.p + c.b0, nullptr, ln.out.p, ctx->d_out_off.p + c.b0,
+                    ctx->d_out_cap.p + c.b0, ctx->d_out_len.p + c.b0, ctx->d_status.p + c.b0, ctx->d_expected.p + c.b0, n,
+                    nullptr};
+        st = launch_decompress(ctx, a, ln.stream, pl.d_tickets + 8 * (ci % kLanes));
+        if (st != LZ4B200_OK) return st;
+        if (contiguous[ci]) {
+            CTX_CUDA(ctx, cudaMemcpyAsync(out + c.a, ln.out.p, c.b - c.a, cudaMemcpyDeviceToHost, ln.stream));
+        } else {
+            for (uint32_t k = c.b0; k < c.b1; k++)
+                if (out_cap[k])
+                    CTX_CUDA(ctx, cudaMemcpyAsync(out + out_off[k], ln.out.p + h_out_off[k], out_cap[k],
+                                                  cudaMemcpyDeviceToHost, ln.stream));
+        }
     }
+    for (int i = 0; i < kLanes; i++) CTX_CUDA(ctx, cudaStreamSynchronize(pl.lane[i].stream));
+    uint32_t *h_len = reinterpret_cast<uint32_t *>(pl.h_status + nb);
+    CTX_CUDA(ctx, cudaMemcpyAsync(pl.h_status, ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s0));
+    CTX_CUDA(ctx, cudaMemcpyAsync(h_len, ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s0));
+    if (err_expected)
+        CTX_CUDA(ctx, cudaMemcpyAsync(pl.h_seg, ctx->d_expected.p, nb * 8, cudaMemcpyDeviceToHost, s0));
+    CTX_CUDA(ctx, cudaStreamSynchronize(s0));
+    memcpy(status, pl.h_status, nb * 4);
+    memcpy(out_len, h_len, nb * 4);
+    if (err_expected) memcpy(err_expected, pl.h_seg, nb * 8);
     return LZ4B200_OK;
 }
 
