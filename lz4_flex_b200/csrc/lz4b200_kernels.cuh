@@ -12,6 +12,9 @@
 #ifndef ENC_V1
 #define ENC_V1 1
 #endif
+#ifndef DEC_DEFER
+#define DEC_DEFER 1
+#endif
 #ifndef DEC_VARIANT_A
 #define DEC_VARIANT_A 1
 #endif
@@ -315,6 +318,10 @@ __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ sr
 }
 
 // Simple walk: one sequence at a time (fast path + checked path).
+//
+// DEC_DEFER: the stores of a short, non-overlapping match are held back until just before the next
+// match is loaded, so the L2/HBM latency of the back-reference read overlaps the next sequence's token
+// walk and literal copy instead of stalling the group at the store (the hottest stall in the profile).
 template <int G>
 __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
                                                          uint32_t cap, uint32_t sub, uint32_t gmask)
@@ -323,6 +330,21 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // decompress.rs:207-209
     const WordView view(src);
     uint32_t ip = 0, op = 0;
+    // measured on B200: deferral pays for 8-lane groups (4 byte-steps per match), not for wider ones
+    constexpr bool kDefer = DEC_DEFER && G <= 8;
+    uint8_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;                // pending match bytes of this lane
+    uint32_t p_at = 0, p_len = 0;                              // pending match: output position, length (0 = none)
+#define FLUSH_PENDING()                                                        \
+    do {                                                                       \
+        if (kDefer && p_len) {                                                           \
+            uint8_t *pd = dst + p_at;                                          \
+            if (sub < p_len) pd[sub] = pv0;                                    \
+            if (sub + G < p_len) pd[sub + G] = pv1;                            \
+            if (sub + 2 * G < p_len) pd[sub + 2 * G] = pv2;                    \
+            if (sub + 3 * G < p_len) pd[sub + 3 * G] = pv3;                    \
+            p_len = 0;                                                         \
+        }                                                                      \
+    } while (0)
     for (;;) {
         if (ip + 8 <= n) {
             const uint32_t v0 = view.ro4(ip);                  // token + (if no literals) offset + ext byte
@@ -334,7 +356,6 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                 const uint32_t dist = v1 & 0xffffu;
                 uint32_t mlen = 4u + (v0 & 15u), adv = 2;
                 if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
-#if DEC_VARIANT_A
                 if ((mlen != 19 + 255) && lit + mlen <= cap - op) {
                     if (lit) {
                         for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
@@ -342,31 +363,31 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                     }
                     if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return r; }
                     if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }
+                    FLUSH_PENDING();
                     __syncwarp(gmask);
-                    copy_match<G>(dst + op, dist, mlen, sub, gmask);
+                    if (kDefer && dist >= mlen && mlen <= 4u * G) {
+                        const uint8_t *from = dst + op - dist;
+                        if (sub < mlen) pv0 = from[sub];
+                        if (sub + G < mlen) pv1 = from[sub + G];
+                        if (sub + 2 * G < mlen) pv2 = from[sub + 2 * G];
+                        if (sub + 3 * G < mlen) pv3 = from[sub + 3 * G];
+                        p_at = op; p_len = mlen;
+                    } else {
+                        copy_match<G>(dst + op, dist, mlen, sub, gmask);
+                    }
                     op += mlen;
                     ip = q + adv;                              // < n because q + 8 <= n
                     continue;
                 }
-#else
-                const uint32_t at = op + lit;
-                if (mlen != 19 + 255 && lit + mlen <= cap - op && dist != 0 && dist <= at) {
-                    if (lit) {
-                        for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
-                    }
-                    __syncwarp(gmask);
-                    copy_match<G>(dst + at, dist, mlen, sub, gmask);
-                    op = at + mlen;
-                    ip = q + adv;                              // < n because q + 8 <= n
-                    continue;
-                }
-#endif
             }
         }
+        FLUSH_PENDING();
         const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
         if (c == 1) break;
         if (c == 2) return r;
     }
+    FLUSH_PENDING();
+#undef FLUSH_PENDING
     r.written = op;
     return r;
 }
@@ -740,6 +761,140 @@ __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ 
 }
 
 
+// v1 with the match.any restricted to the probes the reference really executed (see encode_block).
+template <typename TabT>
+__device__ __forceinline__ uint32_t encode_block_v1r(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
+                                              TabT *tab, bool cont, bool h5)
+{
+    constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
+    const uint32_t lane = lane_id();
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t o = 0;                                             // output cursor
+    if (n < 13) return put_last_literals(dst, src, 0, n, lane);  // compress.rs:343-346
+
+    // table: zero for a fresh table (0 is a legal candidate: position 0), "invalid" when the
+    // block continues a frame stream (entries of earlier blocks can never match).
+    {
+        constexpr uint32_t words = 4096 * sizeof(TabT) / 4;
+        uint32_t fill = cont ? 0xffffffffu : 0u;
+        uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
+        for (uint32_t i = lane; i < words; i += 32) t32[i] = fill;
+        __syncwarp();
+    }
+    const WordView view(src);
+    const uint32_t last_probe = n - 12;
+    uint32_t anchor = 0, cur = 0;
+    if (!cont) {                                                // compress.rs:353-359
+        uint32_t lo, hi; view.ro5(0, lo, hi);
+        uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
+        if (lane == 0) tab[s] = 0;
+        cur = 1;
+        __syncwarp();
+    }
+
+    for (;;) {
+        // ---- probe batches ----------------------------------------------------------------
+        uint32_t base = cur, stride = 1, cand = 0;
+        for (;;) {
+            uint32_t p = base + lane * stride;
+            bool term = p > last_probe;
+            uint32_t key = 0, v4 = 0, cnd = kInvalid;
+            if (!term) {
+                uint32_t hi; view.ro5(p, v4, hi);
+                key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
+                cnd = tab[key];
+            }
+            // speculative candidate check with the value read before any write of this batch
+            bool hit = false;
+            if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
+            uint32_t hits = __ballot_sync(kFull, hit), terms = __ballot_sync(kFull, term);
+            uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
+            // only probes [0, c) were executed by the reference; if their slots are distinct the reads were exact
+            const uint32_t c = win < tfirst ? win + 1u : tfirst;
+            const bool rel = !term && lane < c;
+            const uint32_t relmask = __ballot_sync(kFull, rel);
+            uint32_t same = 0;
+            if (rel) same = __match_any_sync(relmask, key);
+            if (__ballot_sync(kFull, (same & lt_mask) != 0) == 0) {
+                if (win >= tfirst) win = 32u;
+                if (tfirst < 32u && win == 32u)                        // compress.rs:381-384
+                    return o + put_last_literals(dst + o, src, anchor, n, lane);
+                if (rel) tab[key] = (TabT)p;                        // distinct slots: the writes commute
+            } else {
+                // exact path: forward in-batch writes over the whole warp
+                same = __match_any_sync(kFull, term ? (0x10000u | lane) : key);
+                uint32_t prior = same & lt_mask;
+                if (prior) cnd = base + (31u - __clz(prior)) * stride;
+                hit = false;
+                if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
+                hits = __ballot_sync(kFull, hit);
+                win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+                if (tfirst < win)
+                    return o + put_last_literals(dst + o, src, anchor, n, lane);
+                uint32_t upto = win < 32 ? win : 31u;
+                uint32_t le_mask = upto == 31 ? kFull : ((2u << upto) - 1u);
+                uint32_t mine = same & le_mask;
+                if (!term && lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
+            }
+            __syncwarp();
+            if (win < 32) {
+                cur = __shfl_sync(kFull, p, win);
+                cand = __shfl_sync(kFull, cnd, win);
+                break;
+            }
+            base += 32u * stride;
+            stride++;
+        }
+        const uint32_t dist = cur - cand;
+
+        // ---- extend backwards (compress.rs:272-287) ---------------------------------------
+        for (;;) {
+            uint32_t room = min(cand, cur - anchor);                // how far both may step back
+            bool ok = lane < room && __ldg(src + cur - 1 - lane) == __ldg(src + cand - 1 - lane);
+            uint32_t bad = ~__ballot_sync(kFull, ok);
+            uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+            cur -= k; cand -= k;
+            if (k < 32) break;
+        }
+        const uint32_t lit = cur - anchor;
+
+        // ---- extend forwards (compress.rs:156-216), limit n - 6 ---------------------------
+        cur += 4; cand += 4;
+        uint32_t extra = 0;
+        {
+            const uint32_t lim = n - 6;
+            for (;;) {
+                uint32_t q = cur + lane;
+                bool ok = q < lim && __ldg(src + q) == __ldg(src + cand + lane);
+                uint32_t bad = ~__ballot_sync(kFull, ok);
+                uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+                extra += k; cur += k; cand += k;
+                if (k < 32) break;
+            }
+        }
+        // ---- T[H(cur-2)] = cur-2 (compress.rs:460-461) ------------------------------------
+        {
+            uint32_t lo, hi; view.ro5(cur - 2, lo, hi);
+            uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
+            if (lane == 0) tab[s] = (TabT)(cur - 2);
+            __syncwarp();
+        }
+        // ---- emit the sequence (compress.rs:463-486) --------------------------------------
+        if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
+        o++;
+        if (lit >= 15) o += put_ext(dst + o, lit - 15, lane);
+        for (uint32_t i = lane; i < lit; i += 32) dst[o + i] = __ldg(src + anchor + i);
+        o += lit;
+        if (lane == 0) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }
+        o += 2;
+        if (extra >= 15) o += put_ext(dst + o, extra - 15, lane);
+        anchor = cur;
+    }
+}
+
+
+
 __device__ __forceinline__ uint64_t max_output_size_dev(uint32_t n)
 {
     return 20ull + ((uint64_t)n * 110ull) / 100ull;
@@ -766,7 +921,10 @@ lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
             st = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
         } else {
             const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;   // compress.rs:559
-#if ENC_V1
+#if ENC_V1 == 2
+            written = encode_block_v1r<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
+                                             (fl & LZ4B200_BLOCK_CONT) != 0, h5);
+#elif ENC_V1
             written = encode_block_v1<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
                                             (fl & LZ4B200_BLOCK_CONT) != 0, h5);
 #else
