@@ -314,11 +314,15 @@ def run_ours(args):
                    "ratio": comp_bytes / (nb * BLOCK)},
         "compress_mibs": world * mib_rank / (t_c / 1e3), "decompress_mibs": world * mib_rank / (t_d / 1e3),
         "compress_ms": t_c, "decompress_ms": t_d,
+        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        # (profiles/r1_ncu_summary.json): compress 1.713 + 0.249 GB, decompress 2.238 + 1.059 GB
         "roofline": {"kernel": "lz4_compress_blocks<u16,4>", "bound": "hbm", "achieved": ach_c, "peak": peak,
-                     "unit": "GB/s", "frac": ach_c / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": ach_c / peak, "traffic": 1.962e9 if nb == NBLOCKS_DEFAULT else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes},
-        "roofline_decompress": {"kernel": "lz4_decompress_blocks", "bound": "hbm", "achieved": ach_d, "peak": peak,
-                                "unit": "GB/s", "frac": ach_d / peak, "traffic": None, "peak_source": peak_src,
+        "roofline_decompress": {"kernel": "lz4_decompress_blocks<8,0>", "bound": "hbm", "achieved": ach_d, "peak": peak,
+                                "unit": "GB/s", "frac": ach_d / peak,
+                                "traffic": 3.297e9 if nb == NBLOCKS_DEFAULT else None, "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": alg_bytes},
         "cpu_baseline": {"value": cpu_all["roundtrip_mibs"], "unit": "MiB/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_blocks} of the {nb} blocks, compress+decompress, best of 3, "

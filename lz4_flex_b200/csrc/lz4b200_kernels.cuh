@@ -12,6 +12,9 @@
 #ifndef ENC_V1
 #define ENC_V1 1
 #endif
+#ifndef ENC_PROBE_NOEMIT
+#define ENC_PROBE_NOEMIT 0   // timing probe (invalid output): how much of the chain is emission
+#endif
 #ifndef DEC_DEFER
 #define DEC_DEFER 1
 #endif
@@ -747,6 +750,9 @@ __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ 
             if (lane == 0) tab[s] = (TabT)(cur - 2);
             __syncwarp();
         }
+#if ENC_PROBE_NOEMIT
+        o += 3 + lit + (lit >= 15 ? 1 : 0) + (extra >= 15 ? 1 : 0); anchor = cur; continue;   // timing probe only: no output
+#endif
         // ---- emit the sequence (compress.rs:463-486) --------------------------------------
         if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
         o++;

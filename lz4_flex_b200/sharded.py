@@ -56,7 +56,8 @@ def gather_frame(part, part_len: int, info: FrameInfo, rank: int, world: int, gr
     sizes = [int(s.item()) for s in sizes]
     if rank != 0:
         if part_len:
-            dist.send(part[:part_len].contiguous(), dst=0, group=group)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, part[:part_len].contiguous(), 0, group)]):
+                req.wait()
         return None
     header = info.header_bytes()
     total = len(header) + sum(sizes) + 4
@@ -65,10 +66,14 @@ def gather_frame(part, part_len: int, info: FrameInfo, rank: int, world: int, gr
     pos = len(header)
     frame[pos: pos + sizes[0]] = part[: sizes[0]]
     pos += sizes[0]
+    ops = []
     for r in range(1, world):
         if sizes[r]:
-            dist.recv(frame[pos: pos + sizes[r]], src=r, group=group)
+            ops.append(dist.P2POp(dist.irecv, frame[pos: pos + sizes[r]], r, group))
         pos += sizes[r]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     frame[pos: pos + 4] = 0
     return frame
 
