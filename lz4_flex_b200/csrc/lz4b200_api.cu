@@ -252,6 +252,8 @@ struct lz4b200_ctx {
     uint32_t *d_tickets = nullptr;            // 3 x {next, retired}
     int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
     int enc_smem_kb = 0;                      // LZ4B200_ENC_SMEM_KB: shared-memory carve-out used by the encoder
+    int enc16s_ctas_per_sm = 0, enc32s_ctas_per_sm = 0;   // split (matcher+emitter) encoder
+    int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
     int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
     int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
     int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
@@ -279,6 +281,11 @@ namespace {
 #endif
 constexpr int kEnc16Warps = ENC16_WARPS;   // 8 KiB table per warp; 1-warp CTAs give the finest smem granularity
 constexpr int kEnc32Warps = 2;     // 2 x 16 KiB tables per CTA
+#ifndef ENC16_PAIRS
+#define ENC16_PAIRS 3
+#endif
+constexpr int kEnc16Pairs = ENC16_PAIRS;   // split encoder: matcher+emitter pairs per CTA (named barriers: <= 3)
+constexpr int kEnc32Pairs = 2;
 
 #define CTX_CUDA(ctx, call)                                              \
     do {                                                                 \
@@ -343,6 +350,14 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             per_sm = std::max<uint32_t>(1, std::min<uint32_t>(per_sm, (uint32_t)ctx->enc_smem_kb / cta_kb));
         }
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * per_sm);
+#if ENC_SPLIT
+        if (!ctx->enc_single_warp) {
+            want = (a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs;
+            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
+            lz4_compress_blocks_split<uint16_t, kEnc16Pairs>
+                <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
+        } else
+#endif
         lz4_compress_blocks<uint16_t, kEnc16Warps>
             <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, tickets + 2);
         CTX_CUDA(ctx, cudaGetLastError());
@@ -350,6 +365,14 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     if (max_in_len == 0 || max_in_len > 65536u) {
         uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
+#if ENC_SPLIT
+        if (!ctx->enc_single_warp) {
+            want = (a.nblocks + kEnc32Pairs - 1) / kEnc32Pairs;
+            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32s_ctas_per_sm));
+            lz4_compress_blocks_split<uint32_t, kEnc32Pairs>
+                <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
+        } else
+#endif
         lz4_compress_blocks<uint32_t, kEnc32Warps>
             <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
@@ -425,7 +448,13 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
                             kEnc16Warps * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                             &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
-                            kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32");
+                            kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc16s_ctas_per_sm, lz4_compress_blocks_split<uint16_t, kEnc16Pairs>, kEnc16Pairs * 64,
+                            split_smem_bytes<uint16_t, kEnc16Pairs>()), "occupancy enc16 split") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs>, kEnc32Pairs * 64,
+                            split_smem_bytes<uint32_t, kEnc32Pairs>()), "occupancy enc32 split");
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
         fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
@@ -442,6 +471,11 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         int v = atoi(g);
         if (v == 8 || v == 16 || v == 32) ctx->enc_group_override = v;
     }
+    if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
+    if (getenv("LZ4B200_DEBUG"))
+        fprintf(stderr, "lz4b200: SMs %d, CTAs/SM: dec %d, enc16 %d, enc32 %d, enc16-split %d (x%d pairs), enc32-split %d (x%d pairs)\n",
+                ctx->sm_count, ctx->dec_ctas_per_sm, ctx->enc16_ctas_per_sm, ctx->enc32_ctas_per_sm,
+                ctx->enc16s_ctas_per_sm, kEnc16Pairs, ctx->enc32s_ctas_per_sm, kEnc32Pairs);
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_GROUP")) {

@@ -8,9 +8,9 @@
 // cores.  See DESIGN.md for the layout, the per-kernel roofline and what each phase costs.
 #pragma once
 // Build-time variant switches (A/B-measured on B200).
-// ENC_V1=1: first-generation encoder (22.8 ms on config 2) instead of the restricted-match.any one (25.6 ms).
-#ifndef ENC_V1
-#define ENC_V1 1
+// ENC_SPLIT=1: matcher warp + emitter warp per block (lz4_compress_blocks_split); 0: one warp does both (v1).
+#ifndef ENC_SPLIT
+#define ENC_SPLIT 1
 #endif
 #ifndef ENC_PROBE_NOEMIT
 #define ENC_PROBE_NOEMIT 0   // timing probe (invalid output): how much of the chain is emission
@@ -479,177 +479,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
-// Encodes one block with one warp: exact emulation of the reference's sequential greedy parse.
-//
-// One probe batch = up to 32 consecutive probes of the reference's probe loop (compress.rs:373-439),
-// one per lane.  After a match the reference also re-inserts position cur-2 (compress.rs:460-461)
-// before the next probe; that insert rides in lane 0 of the next sequence's first batch, so its
-// input bytes come from the same loads as the probes.
-//
-// The sequential loop reads T[h] and overwrites it with the probe position before the next probe, so
-// a probe can see the write of an earlier probe of the same batch when their hashes collide.  Fast
-// path: every lane reads its slot and fetches the candidate's bytes; with w = first lane whose
-// candidate matches, only lanes 0..w were really executed by the reference.  A match.any restricted to
-// those lanes (cheap: w is small) proves that their hashes are distinct, in which case the values read
-// were exact and their table writes commute.  Otherwise the exact path recomputes every lane's
-// candidate with in-batch forwarding over the whole warp.  Either way the table after the batch and
-// the chosen match equal the reference's.
-template <typename TabT>
-__device__ __forceinline__ uint32_t encode_block(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                                 TabT *tab, bool cont, bool h5)
-{
-    constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
-    const uint32_t lane = lane_id();
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t o = 0;                                             // output cursor
-    if (n < 13) return put_last_literals(dst, src, 0, n, lane);  // compress.rs:343-346
-
-    // table: zero for a fresh table (0 is a legal candidate: position 0), "invalid" when the
-    // block continues a frame stream (entries of earlier blocks can never match).
-    {
-        constexpr uint32_t words = 4096 * sizeof(TabT) / 16;
-        const uint32_t f = cont ? 0xffffffffu : 0u;
-        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
-        for (uint32_t i = lane; i < words; i += 32) t128[i] = make_uint4(f, f, f, f);
-        __syncwarp();
-    }
-    const WordView view(src);
-    const uint32_t last_probe = n - 12;
-    const uint32_t lim = n - 6;                                 // matches end before the last END_OFFSET bytes
-    uint32_t anchor = 0, cur = 0;
-    bool reinsert = false;                                      // T[H(cur-2)] = cur-2 still owed
-    if (!cont) {                                                // compress.rs:353-359
-        uint32_t lo, hi; view.ro5(0, lo, hi);
-        uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) tab[s] = 0;
-        cur = 1;
-        __syncwarp();
-    }
-
-    for (;;) {                                                  // one sequence per iteration
-        if (lane < 2) prefetch_l1(src + min(cur + 192u + 128u * lane, n - 1u));
-        const uint32_t shift = reinsert ? 2u : 0u;              // lanes 0,1 of the first batch: insert, idle
-        const bool regs_hold_literals = anchor == cur;          // false only for the first sequence of a fresh block
-        bool first_batch = true;
-        uint32_t k0 = 0, mpos, cand, v4;
-        for (;;) {                                              // probe batches
-            const uint32_t sh = first_batch ? shift : 0u;
-            const bool ins = sh != 0 && lane == 0;
-            const bool probe = lane >= sh;
-            const uint32_t k = k0 + lane - sh;                  // probe index of this lane
-            const uint32_t kq = k >> 5, kr = k & 31u;           // step of probe j is (32 + j) >> 5
-            uint32_t pos = cur + (16u * kq + kr) * (kq + 1u);
-            if (ins) pos = cur - 2u;
-            const bool term = probe && pos > last_probe;
-            const bool act = ins || (probe && !term);
-            // branch-free: inactive lanes fetch position 0 (always readable: n >= 13) and are masked out below
-            uint32_t hi5;
-            view.ro5(act ? pos : 0u, v4, hi5);
-            const uint32_t key = h5 ? slot_h5(v4, hi5) : slot_h4(v4);
-            const uint32_t old = tab[key];
-            const bool spec = act && probe && old != kInvalid && pos - old <= 65535u;
-            const uint32_t cv = view.ro4(spec ? old : 0u);      // candidate bytes if nothing in this batch interferes
-            const uint32_t hits = __ballot_sync(kFull, spec && cv == v4);
-            const uint32_t terms = __ballot_sync(kFull, term);
-            const uint32_t w = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
-            const uint32_t t = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
-            const uint32_t c = w < t ? w + 1u : t;              // lanes [0, c) are what the reference executed
-            const bool rel = act && lane < c;
-            const uint32_t relmask = __ballot_sync(kFull, rel);
-            uint32_t same = 0;
-            if (rel) same = __match_any_sync(relmask, key);
-            uint32_t win = w < t ? w : 32u, cnd = act ? old : kInvalid;
-            if (__ballot_sync(kFull, (same & lt_mask) != 0) == 0) {
-                if (rel) tab[key] = (TabT)pos;                  // distinct slots: the writes commute
-            } else {
-                // exact path: forward in-batch writes over the whole warp
-                const uint32_t fsame = __match_any_sync(kFull, act ? key : (0x10000u | lane));
-                const uint32_t prior = fsame & lt_mask;
-                if (prior) {
-                    const uint32_t j = 31u - __clz(prior);      // nearest earlier lane with my slot
-                    const uint32_t jk = k0 + j - sh, jq = jk >> 5, jr = jk & 31u;
-                    cnd = (sh != 0 && j == 0) ? cur - 2u : cur + (16u * jq + jr) * (jq + 1u);
-                }
-                bool hit = false;
-                if (probe && !term && cnd != kInvalid && pos - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
-                const uint32_t hits2 = __ballot_sync(kFull, hit);
-                win = hits2 ? (uint32_t)__ffs(hits2) - 1u : 32u;      // term lanes never hit, so win < t
-                const uint32_t upto = win < 32u ? win : 31u;
-                const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
-                const uint32_t mine = fsame & le_mask;
-                if (act && lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)pos;   // last writer wins
-            }
-            __syncwarp();
-            if (win < 32u) {
-                mpos = __shfl_sync(kFull, pos, win);
-                cand = __shfl_sync(kFull, cnd, win);
-                break;
-            }
-            if (t < 32u)                                        // compress.rs:381-384
-                return o + put_last_literals(dst + o, src, anchor, n, lane);
-            k0 += 32u - sh;
-            first_batch = false;
-        }
-        const uint32_t dist = mpos - cand;
-
-        // ---- extend.  The first forward window (4 bytes per lane from mpos+4 / cand+4) is loaded before the
-        //      backward loop so both directions share one memory round trip.
-        uint32_t fbase = mpos + 4;                                  // forward cursor (input side); match side = -dist
-        bool ffull = fbase + 4 * lane + 4 <= lim;                   // this lane's word lies before n - END_OFFSET
-        uint32_t fx = view.ro4(ffull ? fbase + 4 * lane : 0u) ^ view.ro4(ffull ? fbase + 4 * lane - dist : 0u);
-        for (;;) {                                                  // backward: compress.rs:272-287
-            const uint32_t room = min(cand, mpos - anchor);         // how far both may step back
-            const bool ok = lane < room && __ldg(src + mpos - 1 - lane) == __ldg(src + cand - 1 - lane);
-            const uint32_t bad = ~__ballot_sync(kFull, ok);
-            const uint32_t kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
-            mpos -= kb; cand -= kb;
-            if (kb < 32u) break;
-        }
-        const uint32_t lit = mpos - anchor;
-        for (;;) {                                                  // forward: compress.rs:156-216
-            const uint32_t nm = ffull ? (fx ? (uint32_t)(__ffs(fx) - 1) >> 3 : 4u) : 0u;
-            const uint32_t bad = __ballot_sync(kFull, nm < 4u);
-            if (bad) {
-                const uint32_t fl = (uint32_t)__ffs(bad) - 1u;       // first lane whose word stops the match
-                fbase += 4u * fl + __shfl_sync(kFull, nm, fl);
-                break;
-            }
-            fbase += 128u;
-            ffull = fbase + 4 * lane + 4 <= lim;
-            fx = view.ro4(ffull ? fbase + 4 * lane : 0u) ^ view.ro4(ffull ? fbase + 4 * lane - dist : 0u);
-        }
-        if (fbase < lim) {                                          // a word that crossed n - 6: finish bytewise
-            const uint32_t q = fbase + lane;
-            const bool ok = lane < 4u && q < lim && __ldg(src + q) == __ldg(src + q - dist);
-            fbase += (uint32_t)__ffs(~__ballot_sync(kFull, ok)) - 1u;   // lanes >= 4 always stop: at most 3 more bytes
-        }
-        const uint32_t extra = fbase - (mpos + 4);                  // duplicate_length: match bytes beyond MINMATCH
-
-        // ---- emit the sequence (compress.rs:463-486) --------------------------------------
-        const uint32_t hdr = lit >= 15 ? 2u : 1u;                   // token (+ one length byte: lit < 15 + 255 here)
-        if (first_batch && regs_hold_literals) {
-            // literal i sits in the low byte of lane (i + shift)'s probe word: no loads
-            const uint32_t i = lane - shift;
-            if (lane >= shift && i < lit) dst[o + hdr + i] = (uint8_t)v4;
-            if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
-            if (lane == 1 && lit >= 15) dst[o + 1] = (uint8_t)(lit - 15);
-            o += hdr + lit;
-        } else {
-            if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
-            o++;
-            if (lit >= 15) o += put_ext(dst + o, lit - 15, lane);
-            for (uint32_t i = lane; i < lit; i += 32) dst[o + i] = __ldg(src + anchor + i);
-            o += lit;
-        }
-        if (lane == 2) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }
-        o += 2;
-        if (extra >= 15) o += put_ext(dst + o, extra - 15, lane);
-        anchor = cur = fbase;
-        reinsert = true;
-    }
-}
-
-// First-generation encoder (full-warp match.any per batch, byte-wise extension); kept selectable for A/B runs.
+// Single-warp encoder (one warp searches and emits); kept selectable (ENC_SPLIT=0) for A/B runs.
 template <typename TabT>
 __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
                                               TabT *tab, bool cont, bool h5)
@@ -767,140 +597,6 @@ __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ 
 }
 
 
-// v1 with the match.any restricted to the probes the reference really executed (see encode_block).
-template <typename TabT>
-__device__ __forceinline__ uint32_t encode_block_v1r(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                              TabT *tab, bool cont, bool h5)
-{
-    constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
-    const uint32_t lane = lane_id();
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t o = 0;                                             // output cursor
-    if (n < 13) return put_last_literals(dst, src, 0, n, lane);  // compress.rs:343-346
-
-    // table: zero for a fresh table (0 is a legal candidate: position 0), "invalid" when the
-    // block continues a frame stream (entries of earlier blocks can never match).
-    {
-        constexpr uint32_t words = 4096 * sizeof(TabT) / 4;
-        uint32_t fill = cont ? 0xffffffffu : 0u;
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
-        for (uint32_t i = lane; i < words; i += 32) t32[i] = fill;
-        __syncwarp();
-    }
-    const WordView view(src);
-    const uint32_t last_probe = n - 12;
-    uint32_t anchor = 0, cur = 0;
-    if (!cont) {                                                // compress.rs:353-359
-        uint32_t lo, hi; view.ro5(0, lo, hi);
-        uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) tab[s] = 0;
-        cur = 1;
-        __syncwarp();
-    }
-
-    for (;;) {
-        // ---- probe batches ----------------------------------------------------------------
-        uint32_t base = cur, stride = 1, cand = 0;
-        for (;;) {
-            uint32_t p = base + lane * stride;
-            bool term = p > last_probe;
-            uint32_t key = 0, v4 = 0, cnd = kInvalid;
-            if (!term) {
-                uint32_t hi; view.ro5(p, v4, hi);
-                key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
-                cnd = tab[key];
-            }
-            // speculative candidate check with the value read before any write of this batch
-            bool hit = false;
-            if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
-            uint32_t hits = __ballot_sync(kFull, hit), terms = __ballot_sync(kFull, term);
-            uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
-            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
-            // only probes [0, c) were executed by the reference; if their slots are distinct the reads were exact
-            const uint32_t c = win < tfirst ? win + 1u : tfirst;
-            const bool rel = !term && lane < c;
-            const uint32_t relmask = __ballot_sync(kFull, rel);
-            uint32_t same = 0;
-            if (rel) same = __match_any_sync(relmask, key);
-            if (__ballot_sync(kFull, (same & lt_mask) != 0) == 0) {
-                if (win >= tfirst) win = 32u;
-                if (tfirst < 32u && win == 32u)                        // compress.rs:381-384
-                    return o + put_last_literals(dst + o, src, anchor, n, lane);
-                if (rel) tab[key] = (TabT)p;                        // distinct slots: the writes commute
-            } else {
-                // exact path: forward in-batch writes over the whole warp
-                same = __match_any_sync(kFull, term ? (0x10000u | lane) : key);
-                uint32_t prior = same & lt_mask;
-                if (prior) cnd = base + (31u - __clz(prior)) * stride;
-                hit = false;
-                if (!term && cnd != kInvalid && p - cnd <= 65535u) hit = (view.ro4(cnd) == v4);
-                hits = __ballot_sync(kFull, hit);
-                win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
-                if (tfirst < win)
-                    return o + put_last_literals(dst + o, src, anchor, n, lane);
-                uint32_t upto = win < 32 ? win : 31u;
-                uint32_t le_mask = upto == 31 ? kFull : ((2u << upto) - 1u);
-                uint32_t mine = same & le_mask;
-                if (!term && lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
-            }
-            __syncwarp();
-            if (win < 32) {
-                cur = __shfl_sync(kFull, p, win);
-                cand = __shfl_sync(kFull, cnd, win);
-                break;
-            }
-            base += 32u * stride;
-            stride++;
-        }
-        const uint32_t dist = cur - cand;
-
-        // ---- extend backwards (compress.rs:272-287) ---------------------------------------
-        for (;;) {
-            uint32_t room = min(cand, cur - anchor);                // how far both may step back
-            bool ok = lane < room && __ldg(src + cur - 1 - lane) == __ldg(src + cand - 1 - lane);
-            uint32_t bad = ~__ballot_sync(kFull, ok);
-            uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
-            cur -= k; cand -= k;
-            if (k < 32) break;
-        }
-        const uint32_t lit = cur - anchor;
-
-        // ---- extend forwards (compress.rs:156-216), limit n - 6 ---------------------------
-        cur += 4; cand += 4;
-        uint32_t extra = 0;
-        {
-            const uint32_t lim = n - 6;
-            for (;;) {
-                uint32_t q = cur + lane;
-                bool ok = q < lim && __ldg(src + q) == __ldg(src + cand + lane);
-                uint32_t bad = ~__ballot_sync(kFull, ok);
-                uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
-                extra += k; cur += k; cand += k;
-                if (k < 32) break;
-            }
-        }
-        // ---- T[H(cur-2)] = cur-2 (compress.rs:460-461) ------------------------------------
-        {
-            uint32_t lo, hi; view.ro5(cur - 2, lo, hi);
-            uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-            if (lane == 0) tab[s] = (TabT)(cur - 2);
-            __syncwarp();
-        }
-        // ---- emit the sequence (compress.rs:463-486) --------------------------------------
-        if (lane == 0) dst[o] = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));
-        o++;
-        if (lit >= 15) o += put_ext(dst + o, lit - 15, lane);
-        for (uint32_t i = lane; i < lit; i += 32) dst[o + i] = __ldg(src + anchor + i);
-        o += lit;
-        if (lane == 0) { dst[o] = (uint8_t)dist; dst[o + 1] = (uint8_t)(dist >> 8); }
-        o += 2;
-        if (extra >= 15) o += put_ext(dst + o, extra - 15, lane);
-        anchor = cur;
-    }
-}
-
-
-
 __device__ __forceinline__ uint64_t max_output_size_dev(uint32_t n)
 {
     return 20ull + ((uint64_t)n * 110ull) / 100ull;
@@ -927,16 +623,8 @@ lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
             st = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
         } else {
             const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;   // compress.rs:559
-#if ENC_V1 == 2
-            written = encode_block_v1r<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
-                                             (fl & LZ4B200_BLOCK_CONT) != 0, h5);
-#elif ENC_V1
             written = encode_block_v1<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
                                             (fl & LZ4B200_BLOCK_CONT) != 0, h5);
-#else
-            written = encode_block<TabT>(a.in + a.in_off[b], n, a.out + a.out_off[b], tab,
-                                         (fl & LZ4B200_BLOCK_CONT) != 0, h5);
-#endif
         }
         if (lane_id() == 0) { a.out_len[b] = written; a.status[b] = st; }
     }
@@ -944,3 +632,5 @@ lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
 }
 
 }  // namespace lz4b200
+
+#include "lz4b200_enc_split.cuh"
