@@ -283,7 +283,7 @@ def run_ours(args):
     # whole trip host -> GPU compress -> host (compressed) -> GPU decompress -> host inside the timed region.
     import threading
     import queue as _queue
-    ctx2 = block.Context(local)
+    ctx2 = block.Context(local, high_priority=True)      # decode kernels are short: let them jump the encoder's queue
 
     def pipelined(nchunks):
         per = -(-nb // nchunks)

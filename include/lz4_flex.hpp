@@ -168,6 +168,92 @@ inline Result<std::vector<uint8_t>, DecompressError> decompress_size_prepended(c
     return decompress(s.value().second, n - 4, s.value().first, ctx);
 }
 
+// ---- external dictionary (compress.rs:610-616, 685-694; decompress.rs:462-468, 478-528) ----
+
+// block::compress_into_with_dict (compress.rs:610)
+inline Result<size_t, CompressError> compress_into_with_dict(const uint8_t *input, size_t n, uint8_t *output, size_t cap,
+                                                             const uint8_t *dict_data, size_t dict_len,
+                                                             lz4b200_ctx *ctx = nullptr)
+{
+    using R = Result<size_t, CompressError>;
+    if (!ctx) ctx = default_context();
+    if (!ctx) return R::Err({CompressError::Cuda});
+    size_t written = 0;
+    const lz4b200_status st = lz4b200_compress_into_with_dict(ctx, input, n, dict_data, dict_len, output, cap, &written);
+    if (st == LZ4B200_OK) return R::Ok(written);
+    return R::Err({st == LZ4B200_COMPRESS_OUTPUT_TOO_SMALL ? CompressError::OutputTooSmall : CompressError::Cuda});
+}
+
+// block::compress_with_dict (compress.rs:685)
+inline std::vector<uint8_t> compress_with_dict(const uint8_t *input, size_t n, const uint8_t *ext_dict, size_t dict_len,
+                                               lz4b200_ctx *ctx = nullptr)
+{
+    std::vector<uint8_t> out(get_maximum_output_size(n));
+    auto r = compress_into_with_dict(input, n, out.data(), out.size(), ext_dict, dict_len, ctx);
+    out.resize(r.is_ok() ? r.value() : 0);
+    out.shrink_to_fit();
+    return out;
+}
+
+// block::compress_prepend_size_with_dict (compress.rs:692)
+inline std::vector<uint8_t> compress_prepend_size_with_dict(const uint8_t *input, size_t n, const uint8_t *ext_dict,
+                                                            size_t dict_len, lz4b200_ctx *ctx = nullptr)
+{
+    if (!ctx) ctx = default_context();
+    std::vector<uint8_t> out(get_maximum_output_size(n) + 4);
+    size_t written = 0;
+    if (!ctx || lz4b200_compress_prepend_size_with_dict(ctx, input, n, ext_dict, dict_len, out.data(), out.size(),
+                                                        &written) != LZ4B200_OK)
+        written = 0;
+    out.resize(written);
+    out.shrink_to_fit();
+    return out;
+}
+
+// block::decompress_into_with_dict (decompress.rs:462)
+inline Result<size_t, DecompressError> decompress_into_with_dict(const uint8_t *input, size_t n, uint8_t *output,
+                                                                 size_t cap, const uint8_t *ext_dict, size_t dict_len,
+                                                                 lz4b200_ctx *ctx = nullptr)
+{
+    using R = Result<size_t, DecompressError>;
+    if (!ctx) ctx = default_context();
+    if (!ctx) return R::Err({DecompressError::Cuda});
+    size_t written = 0, expected = 0, actual = 0;
+    const lz4b200_status st = lz4b200_decompress_into_with_dict(ctx, input, n, ext_dict, dict_len, output, cap, &written,
+                                                                &expected, &actual);
+    if (st == LZ4B200_OK) return R::Ok(written);
+    DecompressError e;
+    e.kind = (st >= 2 && st <= 6) ? (DecompressError::Kind)st : DecompressError::Cuda;
+    e.expected = expected; e.actual = actual;
+    return R::Err(e);
+}
+
+// block::decompress_with_dict (decompress.rs:478)
+inline Result<std::vector<uint8_t>, DecompressError> decompress_with_dict(const uint8_t *input, size_t n,
+                                                                          size_t min_uncompressed_size,
+                                                                          const uint8_t *ext_dict, size_t dict_len,
+                                                                          lz4b200_ctx *ctx = nullptr)
+{
+    using R = Result<std::vector<uint8_t>, DecompressError>;
+    std::vector<uint8_t> out(min_uncompressed_size);
+    auto r = decompress_into_with_dict(input, n, out.data(), out.size(), ext_dict, dict_len, ctx);
+    if (r.is_err()) return R::Err(r.error());
+    out.resize(r.value());
+    return R::Ok(std::move(out));
+}
+
+// block::decompress_size_prepended_with_dict (decompress.rs:522)
+inline Result<std::vector<uint8_t>, DecompressError> decompress_size_prepended_with_dict(const uint8_t *input, size_t n,
+                                                                                         const uint8_t *ext_dict,
+                                                                                         size_t dict_len,
+                                                                                         lz4b200_ctx *ctx = nullptr)
+{
+    using R = Result<std::vector<uint8_t>, DecompressError>;
+    auto s = uncompressed_size(input, n);
+    if (s.is_err()) return R::Err(s.error());
+    return decompress_with_dict(s.value().second, n - 4, s.value().first, ext_dict, dict_len, ctx);
+}
+
 }  // namespace block
 
 namespace frame {

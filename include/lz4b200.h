@@ -94,6 +94,10 @@ const char *lz4b200_last_cuda_error(const lz4b200_ctx *ctx);
  * Fails with LZ4B200_CUDA_ERROR when no usable device exists — there is no CPU fallback. */
 lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out);
 void lz4b200_ctx_destroy(lz4b200_ctx *ctx);
+/* Ask for the highest CUDA stream priority for this context's host-batch pipelines (call before the first
+ * batch call).  Use it for the decompress side when a compress context keeps the same GPU busy: decode kernels are
+ * short and otherwise queue behind the encoder's long-lived CTAs. */
+void lz4b200_ctx_set_priority(lz4b200_ctx *ctx, int high);
 /* The context's own stream (cudaStream_t). */
 void *lz4b200_ctx_stream(lz4b200_ctx *ctx);
 
@@ -169,6 +173,60 @@ lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx,
 
 lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx,
     const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+    uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+    uint32_t *out_len, int32_t *status, uint64_t *err_expected, size_t nblocks);
+
+/* ---- external dictionary ("_with_dict") -----------------------------------------------------
+ * The dictionary logically precedes the input: the encoder may reference its last 64 KiB, the decoder
+ * resolves offsets that reach before the start of the output inside it.  Like the reference, the
+ * encoder ignores dictionaries of <= 3 bytes (compress.rs:626-628) and everything but the last
+ * WINDOW_SIZE = 65 536 bytes (init_dict, compress.rs:571-575); the table layout / hash follow
+ * dict_len + n (compress.rs:559).  One dictionary is shared by every block of a batch. */
+
+/* block::compress_into_with_dict — src/block/compress.rs:610-616 (compress_with_dict :685-687). */
+lz4b200_status lz4b200_compress_into_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                               const uint8_t *dict, size_t dict_len,
+                                               uint8_t *out, size_t cap, size_t *written);
+
+/* block::compress_prepend_size_with_dict — src/block/compress.rs:692-694. */
+lz4b200_status lz4b200_compress_prepend_size_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                       const uint8_t *dict, size_t dict_len,
+                                                       uint8_t *out, size_t cap, size_t *written);
+
+/* block::decompress_into_with_dict — src/block/decompress.rs:462-468 (copy_from_dict :85-109;
+ * DEC_OFFSET_OUT_OF_BOUNDS when offset > bytes written + dict_len, :287-289/:399-401). */
+lz4b200_status lz4b200_decompress_into_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                 const uint8_t *dict, size_t dict_len,
+                                                 uint8_t *out, size_t cap, size_t *written,
+                                                 size_t *err_expected, size_t *err_actual);
+
+/* block::decompress_size_prepended_with_dict — src/block/decompress.rs:522-528. */
+lz4b200_status lz4b200_decompress_size_prepended_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                           const uint8_t *dict, size_t dict_len,
+                                                           uint8_t *out, size_t cap, size_t *written,
+                                                           size_t *err_expected, size_t *err_actual);
+
+/* Batches with one shared dictionary: device pointers (d_dict on the device) and host pointers. */
+lz4b200_status lz4b200_compress_batch_device_with_dict(lz4b200_ctx *ctx,
+    const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+    const uint8_t *d_dict, size_t dict_len,
+    uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+    uint32_t *d_out_len, int32_t *d_status, size_t nblocks,
+    uint32_t max_in_len, void *stream);
+lz4b200_status lz4b200_decompress_batch_device_with_dict(lz4b200_ctx *ctx,
+    const uint8_t *d_in, const uint64_t *d_in_off, const uint32_t *d_in_len,
+    const uint8_t *d_dict, size_t dict_len,
+    uint8_t *d_out, const uint64_t *d_out_off, const uint32_t *d_out_cap,
+    uint32_t *d_out_len, int32_t *d_status, uint64_t *d_err_expected,
+    size_t nblocks, void *stream);
+lz4b200_status lz4b200_compress_batch_host_with_dict(lz4b200_ctx *ctx,
+    const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+    const uint8_t *dict, size_t dict_len,
+    uint8_t *out, size_t out_cap_total, uint64_t *out_off,
+    uint32_t *out_len, int32_t *status, size_t nblocks);
+lz4b200_status lz4b200_decompress_batch_host_with_dict(lz4b200_ctx *ctx,
+    const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len,
+    const uint8_t *dict, size_t dict_len,
     uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
     uint32_t *out_len, int32_t *status, uint64_t *err_expected, size_t nblocks);
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "lz4b200_last_cuda_error": (C.c_char_p, [_vp]),
     "lz4b200_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
     "lz4b200_ctx_destroy": (None, [_vp]),
+    "lz4b200_ctx_set_priority": (None, [_vp, _i32]),
     "lz4b200_ctx_stream": (_vp, [_vp]),
     "lz4b200_max_output_size": (_sz, [_sz]),
     "lz4b200_compress_into": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz]),
@@ -84,6 +85,14 @@ SIGNATURES = {
     "lz4b200_decompress_batch_device": (_i32, [_vp] * 10 + [_sz, _vp]),
     "lz4b200_compress_batch_host": (_i32, [_vp] * 6 + [_sz] + [_vp] * 3 + [_sz]),
     "lz4b200_decompress_batch_host": (_i32, [_vp] * 10 + [_sz]),
+    "lz4b200_compress_into_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz]),
+    "lz4b200_compress_prepend_size_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz]),
+    "lz4b200_decompress_into_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz, _psz, _psz]),
+    "lz4b200_decompress_size_prepended_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz, _psz, _psz]),
+    "lz4b200_compress_batch_device_with_dict": (_i32, [_vp] * 5 + [_sz] + [_vp] * 5 + [_sz, _u32, _vp]),
+    "lz4b200_decompress_batch_device_with_dict": (_i32, [_vp] * 5 + [_sz] + [_vp] * 6 + [_sz, _vp]),
+    "lz4b200_compress_batch_host_with_dict": (_i32, [_vp] * 5 + [_sz, _vp, _sz] + [_vp] * 3 + [_sz]),
+    "lz4b200_decompress_batch_host_with_dict": (_i32, [_vp] * 5 + [_sz] + [_vp] * 6 + [_sz]),
     "lz4b200_frame_bound": (_sz, [_sz, C.POINTER(FrameInfoC)]),
     "lz4b200_frame_compress": (_i32, [_vp, _vp, _sz, C.POINTER(FrameInfoC), _sz, _vp, _sz, _psz]),
     "lz4b200_frame_compress_blocks_device": (_i32, [_vp, _vp, _sz, _sz, C.c_uint64, _vp, _sz, _vp, _vp, _vp]),

@@ -31,7 +31,7 @@ MAX_DISTANCE = (1 << 16) - 1     # block/mod.rs:64
 class Context:
     """One lz4b200_ctx: a stream plus scratch on one GPU.  Not shareable between threads at the same time."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         L = _native.lib()
         h = C.c_void_p()
         st = L.lz4b200_ctx_create(device, C.byref(h))
@@ -40,6 +40,8 @@ class Context:
                             f"(status {st}); there is no CPU fallback")
         self._h = h
         self.device = device
+        if high_priority:                                   # decode side of a two-context streaming pipeline
+            L.lz4b200_ctx_set_priority(h, 1)
 
     @property
     def handle(self):
@@ -182,6 +184,121 @@ def decompress_size_prepended(input, ctx: Context | None = None) -> bytes:
     """block::decompress_size_prepended (decompress.rs:496)."""
     size, rest = uncompressed_size(input)
     return decompress(rest, size, ctx)
+
+
+# ---- external dictionary ------------------------------------------------------------------------------
+
+def compress_into_with_dict(input, output, dict_data, ctx: Context | None = None) -> int:
+    """block::compress_into_with_dict (compress.rs:610-616)."""
+    ctx = ctx or default_context()
+    src, d = _as_u8(input), _as_u8(dict_data)
+    dst = _as_u8(output) if isinstance(output, np.ndarray) else np.frombuffer(output, dtype=np.uint8)
+    w = C.c_size_t(0)
+    st = _native.lib().lz4b200_compress_into_with_dict(ctx.handle, _ptr(src), src.size, _ptr(d), d.size, _ptr(dst),
+                                                       dst.size, C.byref(w))
+    if st != 0:
+        _raise(ctx, st)
+    return w.value
+
+
+def compress_with_dict(input, ext_dict, ctx: Context | None = None) -> bytes:
+    """block::compress_with_dict (compress.rs:685-687)."""
+    src = _as_u8(input)
+    out = np.empty(get_maximum_output_size(src.size), dtype=np.uint8)
+    n = compress_into_with_dict(src, out, ext_dict, ctx)
+    return out[:n].tobytes()
+
+
+def compress_prepend_size_with_dict(input, ext_dict, ctx: Context | None = None) -> bytes:
+    """block::compress_prepend_size_with_dict (compress.rs:692-694)."""
+    ctx = ctx or default_context()
+    src, d = _as_u8(input), _as_u8(ext_dict)
+    out = np.empty(get_maximum_output_size(src.size) + 4, dtype=np.uint8)
+    w = C.c_size_t(0)
+    st = _native.lib().lz4b200_compress_prepend_size_with_dict(ctx.handle, _ptr(src), src.size, _ptr(d), d.size,
+                                                               _ptr(out), out.size, C.byref(w))
+    if st != 0:
+        _raise(ctx, st)
+    return out[: w.value].tobytes()
+
+
+def decompress_into_with_dict(input, output, ext_dict, ctx: Context | None = None) -> int:
+    """block::decompress_into_with_dict (decompress.rs:462-468)."""
+    ctx = ctx or default_context()
+    src, d = _as_u8(input), _as_u8(ext_dict)
+    dst = _as_u8(output) if isinstance(output, np.ndarray) else np.frombuffer(output, dtype=np.uint8)
+    w, e1, e2 = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    st = _native.lib().lz4b200_decompress_into_with_dict(ctx.handle, _ptr(src), src.size, _ptr(d), d.size, _ptr(dst),
+                                                         dst.size, C.byref(w), C.byref(e1), C.byref(e2))
+    if st != 0:
+        _raise(ctx, st, e1.value, e2.value)
+    return w.value
+
+
+def decompress_with_dict(input, min_uncompressed_size: int, ext_dict, ctx: Context | None = None) -> bytes:
+    """block::decompress_with_dict (decompress.rs:478-490)."""
+    out = np.empty(max(min_uncompressed_size, 0), dtype=np.uint8)
+    n = decompress_into_with_dict(input, out, ext_dict, ctx)
+    return out[:n].tobytes()
+
+
+def decompress_size_prepended_with_dict(input, ext_dict, ctx: Context | None = None) -> bytes:
+    """block::decompress_size_prepended_with_dict (decompress.rs:522-528)."""
+    size, rest = uncompressed_size(input)
+    return decompress_with_dict(rest, size, ext_dict, ctx)
+
+
+def compress_blocks_with_dict(blocks: Iterable[bytes], ext_dict, ctx: Context | None = None) -> list[bytes]:
+    """Many independent blocks sharing one dictionary, one launch (lz4b200_compress_batch_host_with_dict)."""
+    ctx = ctx or default_context()
+    blocks = [bytes(b) for b in blocks]
+    d = _as_u8(ext_dict)
+    lens = np.array([len(b) for b in blocks], dtype=np.uint32)
+    offs = np.zeros(len(blocks), dtype=np.uint64)
+    if len(blocks) > 1:
+        offs[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    src = np.frombuffer(b"".join(blocks) or b"\0", dtype=np.uint8)
+    cap = int(sum(get_maximum_output_size(int(x)) for x in lens))
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    out_off = np.zeros(len(blocks), dtype=np.uint64)
+    out_len = np.zeros(len(blocks), dtype=np.uint32)
+    status = np.zeros(len(blocks), dtype=np.int32)
+    st = _native.lib().lz4b200_compress_batch_host_with_dict(
+        ctx.handle, _ptr(src), _ptr(offs), _ptr(lens), _ptr(d), d.size, _ptr(out), out.size, _ptr(out_off),
+        _ptr(out_len), _ptr(status), len(blocks))
+    if st != 0:
+        _raise(ctx, st)
+    bad = np.nonzero(status)[0]
+    if bad.size:
+        _raise(ctx, int(status[bad[0]]))
+    return [out[int(o): int(o) + int(l)].tobytes() for o, l in zip(out_off, out_len)]
+
+
+def decompress_blocks_with_dict(blocks: Iterable[bytes], caps: Sequence[int], ext_dict, ctx: Context | None = None):
+    """Many independent blocks sharing one dictionary; returns (outputs, status[], expected[])."""
+    ctx = ctx or default_context()
+    blocks = [bytes(b) for b in blocks]
+    d = _as_u8(ext_dict)
+    lens = np.array([len(b) for b in blocks], dtype=np.uint32)
+    offs = np.zeros(len(blocks), dtype=np.uint64)
+    if len(blocks) > 1:
+        offs[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    src = np.frombuffer(b"".join(blocks) or b"\0", dtype=np.uint8)
+    caps = np.asarray(caps, dtype=np.uint32)
+    ooff = np.zeros(len(blocks), dtype=np.uint64)
+    if len(blocks) > 1:
+        ooff[1:] = np.cumsum(caps[:-1].astype(np.uint64))
+    out = np.zeros(max(int(caps.astype(np.uint64).sum()), 1), dtype=np.uint8)
+    out_len = np.zeros(len(blocks), dtype=np.uint32)
+    status = np.zeros(len(blocks), dtype=np.int32)
+    expected = np.zeros(len(blocks), dtype=np.uint64)
+    st = _native.lib().lz4b200_decompress_batch_host_with_dict(
+        ctx.handle, _ptr(src), _ptr(offs), _ptr(lens), _ptr(d), d.size, _ptr(out), _ptr(ooff), _ptr(caps),
+        _ptr(out_len), _ptr(status), _ptr(expected), len(blocks))
+    if st != 0:
+        _raise(ctx, st)
+    outs = [out[int(o): int(o) + int(l)].tobytes() for o, l in zip(ooff, out_len)]
+    return outs, status, expected
 
 
 # ---- many blocks, host memory ----------------------------------------------------------------------

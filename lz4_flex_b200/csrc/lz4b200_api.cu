@@ -253,6 +253,7 @@ struct lz4b200_ctx {
     int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
     int enc_smem_kb = 0;                      // LZ4B200_ENC_SMEM_KB: shared-memory carve-out used by the encoder
     int enc16s_ctas_per_sm = 0, enc32s_ctas_per_sm = 0;   // split (matcher+emitter) encoder
+    int high_priority = 0;                    // lz4b200_ctx_set_priority(ctx, 1): pipeline streams get the highest priority
     int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
     int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
     int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
@@ -261,9 +262,10 @@ struct lz4b200_ctx {
     std::string last_error;
 
     // scratch for host-pointer and frame entry points
-    DevBuf<uint8_t> d_in, d_out, d_slots, d_flags, d_pick;
+    DevBuf<uint8_t> d_in, d_out, d_slots, d_flags, d_pick, d_dict;
     DevBuf<uint64_t> d_in_off, d_out_off, d_seg_off, d_expected, d_off_b;
-    DevBuf<uint32_t> d_in_len, d_out_cap, d_out_len, d_info, d_seg_size, d_payload_len;
+    DevBuf<uint32_t> d_in_len, d_out_cap, d_out_len, d_info, d_seg_size, d_payload_len, d_link_first, d_stored_len, d_done;
+    DevBuf<uint64_t> d_stored_off;
     DevBuf<int32_t> d_status;
 
     bool check(cudaError_t e, const char *what)
@@ -304,8 +306,9 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
     const uint32_t per_cta = kDecWarpsPerCta * (32 / G);
     uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * (ctx->dec_ctas_override ? ctx->dec_ctas_override : 16)));
-    if (ctx->dec_batched) lz4_decompress_blocks<G, 1><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
-    else lz4_decompress_blocks<G, 0><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    else if (ctx->dec_batched) lz4_decompress_blocks<G, 1, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    else lz4_decompress_blocks<G, 0, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     CTX_CUDA(ctx, cudaGetLastError());
     return LZ4B200_OK;
 }
@@ -351,26 +354,34 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         }
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * per_sm);
 #if ENC_SPLIT
-        if (!ctx->enc_single_warp) {
+        if (!ctx->enc_single_warp || a.dict_len) {
             want = (a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs;
             grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
-            lz4_compress_blocks_split<uint16_t, kEnc16Pairs>
-                <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
+            if (a.dict_len)
+                lz4_compress_blocks_split<uint16_t, kEnc16Pairs, true>
+                    <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
+            else
+                lz4_compress_blocks_split<uint16_t, kEnc16Pairs, false>
+                    <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
         } else
 #endif
         lz4_compress_blocks<uint16_t, kEnc16Warps>
             <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, tickets + 2);
         CTX_CUDA(ctx, cudaGetLastError());
     }
-    if (max_in_len == 0 || max_in_len > 65536u) {
+    if (max_in_len == 0 || (uint64_t)max_in_len + a.dict_len > 65536u) {
         uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
 #if ENC_SPLIT
-        if (!ctx->enc_single_warp) {
+        if (!ctx->enc_single_warp || a.dict_len) {
             want = (a.nblocks + kEnc32Pairs - 1) / kEnc32Pairs;
             grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32s_ctas_per_sm));
-            lz4_compress_blocks_split<uint32_t, kEnc32Pairs>
-                <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
+            if (a.dict_len)
+                lz4_compress_blocks_split<uint32_t, kEnc32Pairs, true>
+                    <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
+            else
+                lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>
+                    <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
         } else
 #endif
         lz4_compress_blocks<uint32_t, kEnc32Warps>
@@ -441,7 +452,7 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
               ctx->check(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tickets), 8 * sizeof(uint32_t)), "tickets") &&
               ctx->check(cudaMemset(ctx->d_tickets, 0, 8 * sizeof(uint32_t)), "tickets memset");
     if (ok) {
-        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0>,
+        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0, false>,
                                                                       kDecWarpsPerCta * 32, 0), "occupancy dec") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                             &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
@@ -450,10 +461,10 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
                             &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
                             kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc16s_ctas_per_sm, lz4_compress_blocks_split<uint16_t, kEnc16Pairs>, kEnc16Pairs * 64,
+                            &ctx->enc16s_ctas_per_sm, lz4_compress_blocks_split<uint16_t, kEnc16Pairs, false>, kEnc16Pairs * 64,
                             split_smem_bytes<uint16_t, kEnc16Pairs>()), "occupancy enc16 split") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs>, kEnc32Pairs * 64,
+                            &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>, kEnc32Pairs * 64,
                             split_smem_bytes<uint32_t, kEnc32Pairs>()), "occupancy enc32 split");
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
@@ -499,6 +510,11 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
     ctx->d_in_len.release(); ctx->d_out_cap.release(); ctx->d_out_len.release(); ctx->d_info.release();
     ctx->d_seg_size.release(); ctx->d_payload_len.release(); ctx->d_status.release();
     delete ctx;
+}
+
+void lz4b200_ctx_set_priority(lz4b200_ctx *ctx, int high)
+{
+    if (ctx && !ctx->pipe) ctx->high_priority = high != 0;    // takes effect when the pipeline streams are created
 }
 
 void *lz4b200_ctx_stream(lz4b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -565,6 +581,48 @@ lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *
     return launch_decompress(ctx, a, (cudaStream_t)stream);
 }
 
+// Device-pointer batches with an external dictionary shared by every block (d_dict: the LAST min(len, 65536)
+// bytes of the dictionary, already on the device; compress drops dictionaries of <= 3 bytes like the reference).
+lz4b200_status lz4b200_compress_batch_device_with_dict(lz4b200_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off,
+                                                       const uint32_t *d_in_len, const uint8_t *d_dict, size_t dict_len,
+                                                       uint8_t *d_out, const uint64_t *d_out_off,
+                                                       const uint32_t *d_out_cap, uint32_t *d_out_len,
+                                                       int32_t *d_status, size_t nblocks, uint32_t max_in_len,
+                                                       void *stream)
+{
+    if (!ctx || nblocks > 0xffffffffull || (!d_dict && dict_len)) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks && (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len || !d_status))
+        return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    BatchArgs a{d_in, d_in_off, d_in_len, nullptr, d_out, d_out_off, d_out_cap, d_out_len, d_status, nullptr,
+                (uint32_t)nblocks, nullptr};
+    if (dict_len > 3) {
+        if (dict_len > 65536) { d_dict += dict_len - 65536; dict_len = 65536; }
+        a.dict = d_dict; a.dict_len = (uint32_t)dict_len;
+    }
+    return launch_compress(ctx, a, max_in_len, (cudaStream_t)stream);
+}
+
+lz4b200_status lz4b200_decompress_batch_device_with_dict(lz4b200_ctx *ctx, const uint8_t *d_in,
+                                                         const uint64_t *d_in_off, const uint32_t *d_in_len,
+                                                         const uint8_t *d_dict, size_t dict_len, uint8_t *d_out,
+                                                         const uint64_t *d_out_off, const uint32_t *d_out_cap,
+                                                         uint32_t *d_out_len, int32_t *d_status,
+                                                         uint64_t *d_err_expected, size_t nblocks, void *stream)
+{
+    if (!ctx || nblocks > 0xffffffffull || (!d_dict && dict_len)) return LZ4B200_INVALID_ARGUMENT;
+    if (nblocks && (!d_in || !d_in_off || !d_in_len || !d_out || !d_out_off || !d_out_cap || !d_out_len || !d_status))
+        return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    BatchArgs a{d_in, d_in_off, d_in_len, nullptr, d_out, d_out_off, d_out_cap, d_out_len, d_status, d_err_expected,
+                (uint32_t)nblocks, nullptr};
+    if (dict_len) {
+        if (dict_len > 65536) { d_dict += dict_len - 65536; dict_len = 65536; }
+        a.dict = d_dict; a.dict_len = (uint32_t)dict_len;
+    }
+    return launch_decompress(ctx, a, (cudaStream_t)stream);
+}
+
 // ---- host batch entry points --------------------------------------------------------------------
 // Both calls are chunked software pipelines over kLanes streams: while chunk c runs its kernel, chunk
 // c+1's input crosses PCIe host->device and chunk c-1's result crosses device->host (full duplex), so
@@ -574,11 +632,28 @@ lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx, const uint8_t *
 
 namespace {
 
-constexpr int kLanes = 3;
-constexpr uint64_t kChunkBytes = 32ull << 20;            // decompress: PCIe-bound, small chunks pipeline best
+constexpr int kMaxLanes = 8;
+// Lanes in flight.  A compress chunk occupies its lane for H2D + kernel (one block's serial chain, ~5 ms) + the
+// size read-back + D2H, ~10 ms in all, so three lanes cap the call at ~3.5 ms per 128 MiB chunk whatever the
+// kernel does (measured 30 ms per GiB); six lanes leave the kernel / PCIe as the bound.  LZ4B200_LANES overrides.
+static int lanes_in_use()
+{
+    static const int v = [] { const char *e = getenv("LZ4B200_LANES"); int k = e ? atoi(e) : 6; return k < 1 ? 1 : (k > kMaxLanes ? kMaxLanes : k); }();
+    return v;
+}
+// decompress: a chunk's kernel lasts at least one block's serial chain (~1 ms for 64 KiB of JSON) however few blocks
+// it holds, so chunks must be big enough for that to hide behind the chunk's own D2H copy (2.3 ms per 128 MiB)
+constexpr uint64_t kChunkBytesDefault = 128ull << 20;
 // compress: a 64 KiB block is one ~5 ms serial chain whatever the batch size, so a chunk must hold enough blocks
 // (2048 = 58 % of the resident warps) for two chunks in flight to fill the GPU
-constexpr uint64_t kCompressChunkBytes = 128ull << 20;
+constexpr uint64_t kCompressChunkBytesDefault = 128ull << 20;
+
+uint64_t env_mib(const char *name, uint64_t dflt)         // tuning aid: chunk sizes in MiB
+{
+    const char *v = getenv(name);
+    const long m = v ? atol(v) : 0;
+    return m > 0 ? (uint64_t)m << 20 : dflt;
+}
 
 struct Lane {
     cudaStream_t stream = nullptr;
@@ -587,9 +662,9 @@ struct Lane {
 };
 
 struct Pipeline {
-    Lane lane[kLanes];
+    Lane lane[kMaxLanes];
     cudaEvent_t desc_ready = nullptr;
-    uint32_t *d_tickets = nullptr;           // kLanes x 8 counters
+    uint32_t *d_tickets = nullptr;           // kMaxLanes x 8 counters
     uint64_t *h_seg = nullptr; size_t h_seg_cap = 0;       // pinned
     int32_t *h_status = nullptr; size_t h_status_cap = 0;  // pinned
     bool ready = false;
@@ -598,13 +673,18 @@ struct Pipeline {
 lz4b200_status pipeline_init(lz4b200_ctx *ctx, Pipeline &p)
 {
     if (p.ready) return LZ4B200_OK;
-    for (int i = 0; i < kLanes; i++) {
-        CTX_CUDA(ctx, cudaStreamCreateWithFlags(&p.lane[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxLanes; i++) {
+        // LZ4B200_STREAM_PRIORITY=high: this context's kernels get the SM slots first when another context (e.g. a
+        // compress pipeline running next to a decompress pipeline) keeps the GPU full
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int prio = ctx->high_priority ? hi : 0;
+        CTX_CUDA(ctx, cudaStreamCreateWithPriority(&p.lane[i].stream, cudaStreamNonBlocking, prio));
         CTX_CUDA(ctx, cudaEventCreateWithFlags(&p.lane[i].sizes_ready, cudaEventDisableTiming));
     }
     CTX_CUDA(ctx, cudaEventCreateWithFlags(&p.desc_ready, cudaEventDisableTiming));
-    CTX_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&p.d_tickets), kLanes * 8 * sizeof(uint32_t)));
-    CTX_CUDA(ctx, cudaMemset(p.d_tickets, 0, kLanes * 8 * sizeof(uint32_t)));
+    CTX_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&p.d_tickets), kMaxLanes * 8 * sizeof(uint32_t)));
+    CTX_CUDA(ctx, cudaMemset(p.d_tickets, 0, kMaxLanes * 8 * sizeof(uint32_t)));
     p.ready = true;
     return LZ4B200_OK;
 }
@@ -633,7 +713,7 @@ static void pipeline_destroy(void *vp)
 {
     Pipeline *p = static_cast<Pipeline *>(vp);
     if (!p) return;
-    for (int i = 0; i < kLanes; i++) {
+    for (int i = 0; i < kMaxLanes; i++) {
         if (p->lane[i].stream) { cudaStreamSynchronize(p->lane[i].stream); cudaStreamDestroy(p->lane[i].stream); }
         if (p->lane[i].sizes_ready) cudaEventDestroy(p->lane[i].sizes_ready);
         p->lane[i].in.release(); p->lane[i].slots.release(); p->lane[i].out.release();
@@ -645,23 +725,31 @@ static void pipeline_destroy(void *vp)
     delete p;
 }
 
-extern "C" {
+// The reference keeps only the last WINDOW_SIZE bytes of a dictionary (init_dict, compress.rs:571-575) and drops
+// dictionaries of <= 3 bytes (compress_into_vec_with_dict, compress.rs:626-628).
+static void normalize_dict(const uint8_t *&dict, size_t &dict_len, bool for_compress)
+{
+    if (!dict || (for_compress && dict_len <= 3)) { dict = nullptr; dict_len = 0; return; }
+    if (dict_len > 65536) { dict += dict_len - 65536; dict_len = 65536; }
+}
 
-lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
-                                           const uint32_t *in_len, const uint8_t *flags, uint8_t *out,
-                                           size_t out_cap_total, uint64_t *out_off, uint32_t *out_len,
-                                           int32_t *status, size_t nblocks)
+static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                               const uint32_t *in_len, const uint8_t *flags, const uint8_t *dict,
+                                               size_t dict_len, uint8_t *out, size_t out_cap_total, uint64_t *out_off,
+                                               uint32_t *out_len, int32_t *status, size_t nblocks)
 {
     if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
     if (nblocks == 0) return LZ4B200_OK;
     if (!in || !in_off || !in_len || !out || !out_off || !out_len || !status) return LZ4B200_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
     Pipeline &pl = ctx_pipeline(ctx);
+    const int kLanes = lanes_in_use();
     lz4b200_status st = pipeline_init(ctx, pl);
     if (st != LZ4B200_OK) return st;
     const uint32_t nb = (uint32_t)nblocks;
 
-    // ---- plan: chunks of ~kChunkBytes input, descriptors relative to each chunk's buffers ------
+    // ---- plan: chunks of ~kCompressChunkBytes input, descriptors relative to each chunk's buffers ------
+    static const uint64_t kCompressChunkBytes = env_mib("LZ4B200_ENC_CHUNK_MB", kCompressChunkBytesDefault);
     std::vector<Chunk> chunks;
     std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
     std::vector<uint32_t> h_cap(nb);
@@ -700,6 +788,11 @@ lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, 
     CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
     CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s0));
     if (flags) CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_flags.p, flags, nb, cudaMemcpyHostToDevice, s0));
+    normalize_dict(dict, dict_len, true);
+    if (dict_len) {
+        CTX_CUDA(ctx, ctx->d_dict.reserve(dict_len + 16));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_dict.p, dict, dict_len, cudaMemcpyHostToDevice, s0));
+    }
     CTX_CUDA(ctx, cudaEventRecord(pl.desc_ready, s0));
     CTX_CUDA(ctx, cudaStreamSynchronize(s0));            // the host vectors above may go out of scope before use otherwise
 
@@ -714,6 +807,7 @@ lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, 
         BatchArgs a{ln.in.p, ctx->d_in_off.p + c.b0, ctx->d_in_len.p + c.b0, flags ? ctx->d_flags.p + c.b0 : nullptr,
                     ln.slots.p, ctx->d_out_off.p + c.b0, ctx->d_out_cap.p + c.b0, ctx->d_out_len.p + c.b0,
                     ctx->d_status.p + c.b0, nullptr, n, nullptr};
+        if (dict_len) { a.dict = ctx->d_dict.p; a.dict_len = (uint32_t)dict_len; }
         lz4b200_status r = launch_compress(ctx, a, max_len, ln.stream, pl.d_tickets + 8 * (ci % kLanes));
         if (r != LZ4B200_OK) return r;
         scan_sizes_kernel<<<1, 1024, 0, ln.stream>>>(ctx->d_out_len.p + c.b0, ctx->d_seg_off.p + c.b0 + ci, n);
@@ -764,10 +858,11 @@ lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, 
     return LZ4B200_OK;
 }
 
-lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
-                                             const uint32_t *in_len, uint8_t *out, const uint64_t *out_off,
-                                             const uint32_t *out_cap, uint32_t *out_len, int32_t *status,
-                                             uint64_t *err_expected, size_t nblocks)
+static lz4b200_status decompress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                                 const uint32_t *in_len, const uint8_t *dict, size_t dict_len,
+                                                 uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                                 uint32_t *out_len, int32_t *status, uint64_t *err_expected,
+                                                 size_t nblocks)
 {
     if (!ctx || nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
     if (nblocks == 0) return LZ4B200_OK;
@@ -775,10 +870,12 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in
         return LZ4B200_INVALID_ARGUMENT;
     DeviceGuard guard(ctx->device);
     Pipeline &pl = ctx_pipeline(ctx);
+    const int kLanes = lanes_in_use();
     lz4b200_status st = pipeline_init(ctx, pl);
     if (st != LZ4B200_OK) return st;
     const uint32_t nb = (uint32_t)nblocks;
 
+    static const uint64_t kChunkBytes = env_mib("LZ4B200_DEC_CHUNK_MB", kChunkBytesDefault);
     std::vector<Chunk> chunks;
     std::vector<uint8_t> contiguous;
     std::vector<uint64_t> h_in_off(nb), h_out_off(nb);
@@ -810,6 +907,11 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in
     CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, in_len, nb * 4, cudaMemcpyHostToDevice, s0));
     CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_out_off.data(), nb * 8, cudaMemcpyHostToDevice, s0));
     CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, out_cap, nb * 4, cudaMemcpyHostToDevice, s0));
+    normalize_dict(dict, dict_len, false);
+    if (dict_len) {
+        CTX_CUDA(ctx, ctx->d_dict.reserve(dict_len + 16));
+        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_dict.p, dict, dict_len, cudaMemcpyHostToDevice, s0));
+    }
     CTX_CUDA(ctx, cudaEventRecord(pl.desc_ready, s0));
     CTX_CUDA(ctx, cudaStreamSynchronize(s0));
 
@@ -824,6 +926,7 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in
         BatchArgs a{ln.in.p, ctx->d_in_off.p + c.b0, ctx->d_in_len.p + c.b0, nullptr, ln.out.p, ctx->d_out_off.p + c.b0,
                     ctx->d_out_cap.p + c.b0, ctx->d_out_len.p + c.b0, ctx->d_status.p + c.b0, ctx->d_expected.p + c.b0, n,
                     nullptr};
+        if (dict_len) { a.dict = ctx->d_dict.p; a.dict_len = (uint32_t)dict_len; }
         st = launch_decompress(ctx, a, ln.stream, pl.d_tickets + 8 * (ci % kLanes));
         if (st != LZ4B200_OK) return st;
         if (contiguous[ci]) {
@@ -846,6 +949,45 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in
     memcpy(out_len, h_len, nb * 4);
     if (err_expected) memcpy(err_expected, pl.h_seg, nb * 8);
     return LZ4B200_OK;
+}
+
+extern "C" {
+
+lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                           const uint32_t *in_len, const uint8_t *flags, uint8_t *out,
+                                           size_t out_cap_total, uint64_t *out_off, uint32_t *out_len,
+                                           int32_t *status, size_t nblocks)
+{
+    return compress_batch_host_impl(ctx, in, in_off, in_len, flags, nullptr, 0, out, out_cap_total, out_off, out_len,
+                                    status, nblocks);
+}
+
+lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                             const uint32_t *in_len, uint8_t *out, const uint64_t *out_off,
+                                             const uint32_t *out_cap, uint32_t *out_len, int32_t *status,
+                                             uint64_t *err_expected, size_t nblocks)
+{
+    return decompress_batch_host_impl(ctx, in, in_off, in_len, nullptr, 0, out, out_off, out_cap, out_len, status,
+                                      err_expected, nblocks);
+}
+
+lz4b200_status lz4b200_compress_batch_host_with_dict(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                                     const uint32_t *in_len, const uint8_t *dict, size_t dict_len,
+                                                     uint8_t *out, size_t out_cap_total, uint64_t *out_off,
+                                                     uint32_t *out_len, int32_t *status, size_t nblocks)
+{
+    return compress_batch_host_impl(ctx, in, in_off, in_len, nullptr, dict, dict_len, out, out_cap_total, out_off,
+                                    out_len, status, nblocks);
+}
+
+lz4b200_status lz4b200_decompress_batch_host_with_dict(lz4b200_ctx *ctx, const uint8_t *in, const uint64_t *in_off,
+                                                       const uint32_t *in_len, const uint8_t *dict, size_t dict_len,
+                                                       uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
+                                                       uint32_t *out_len, int32_t *status, uint64_t *err_expected,
+                                                       size_t nblocks)
+{
+    return decompress_batch_host_impl(ctx, in, in_off, in_len, dict, dict_len, out, out_off, out_cap, out_len, status,
+                                      err_expected, nblocks);
 }
 
 // ---- single-block host entry points -----------------------------------------------------------
@@ -905,6 +1047,81 @@ lz4b200_status lz4b200_decompress_into(lz4b200_ctx *ctx, const uint8_t *in, size
     }
     *written = out_len;
     return LZ4B200_OK;
+}
+
+// ---- external dictionary (compress.rs:610-616, 685-693; decompress.rs:462-468, 478-528) ------------------
+
+lz4b200_status lz4b200_compress_into_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n, const uint8_t *dict,
+                                               size_t dict_len, uint8_t *out, size_t cap, size_t *written)
+{
+    if (!ctx || !written || (!in && n) || n > 0xffffffffull || (!dict && dict_len)) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (cap < lz4b200_max_output_size(n)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;     // compress.rs:338-340
+    uint64_t in_off = 0, out_off = 0;
+    uint32_t in_len = (uint32_t)n, out_len = 0;
+    int32_t status = 0;
+    static const uint8_t zero = 0;
+    lz4b200_status st = compress_batch_host_impl(ctx, n ? in : &zero, &in_off, &in_len, nullptr, dict, dict_len, out, cap,
+                                                 &out_off, &out_len, &status, 1);
+    if (st != LZ4B200_OK) return st;
+    if (status != LZ4B200_OK) return (lz4b200_status)status;
+    *written = out_len;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_compress_prepend_size_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                       const uint8_t *dict, size_t dict_len, uint8_t *out, size_t cap,
+                                                       size_t *written)
+{
+    if (!written) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (cap < 4) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    wr32(out, (uint32_t)n);
+    size_t w = 0;
+    lz4b200_status st = lz4b200_compress_into_with_dict(ctx, in, n, dict, dict_len, out + 4, cap - 4, &w);
+    if (st == LZ4B200_OK) *written = w + 4;
+    return st;
+}
+
+lz4b200_status lz4b200_decompress_into_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n, const uint8_t *dict,
+                                                 size_t dict_len, uint8_t *out, size_t cap, size_t *written,
+                                                 size_t *err_expected, size_t *err_actual)
+{
+    if (!ctx || !written || n > 0xffffffffull || cap > 0xffffffffull || (!dict && dict_len)) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (err_expected) *err_expected = 0;
+    if (err_actual) *err_actual = 0;
+    if (n == 0) return LZ4B200_DEC_EXPECTED_ANOTHER_BYTE;                                // decompress.rs:207-209
+    uint64_t in_off = 0, out_off = 0, expected = 0;
+    uint32_t in_len = (uint32_t)n, out_cap = (uint32_t)cap, out_len = 0;
+    int32_t status = 0;
+    uint8_t dummy = 0;
+    lz4b200_status st = decompress_batch_host_impl(ctx, in, &in_off, &in_len, dict, dict_len, cap ? out : &dummy, &out_off,
+                                                   &out_cap, &out_len, &status, &expected, 1);
+    if (st != LZ4B200_OK) return st;
+    if (status != LZ4B200_OK) {
+        if (status == LZ4B200_DEC_OUTPUT_TOO_SMALL) {
+            if (err_expected) *err_expected = (size_t)expected;
+            if (err_actual) *err_actual = cap;
+        }
+        return (lz4b200_status)status;
+    }
+    *written = out_len;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_decompress_size_prepended_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                           const uint8_t *dict, size_t dict_len, uint8_t *out,
+                                                           size_t cap, size_t *written, size_t *err_expected,
+                                                           size_t *err_actual)
+{
+    size_t want = 0;
+    if (written) *written = 0;
+    lz4b200_status st = lz4b200_uncompressed_size(in, n, &want);
+    if (st != LZ4B200_OK) return st;
+    if (cap < want) return LZ4B200_INVALID_ARGUMENT;
+    return lz4b200_decompress_into_with_dict(ctx, in + 4, n - 4, dict, dict_len, out, want, written, err_expected,
+                                             err_actual);
 }
 
 lz4b200_status lz4b200_uncompressed_size(const uint8_t *in, size_t n, size_t *size)
@@ -1080,6 +1297,7 @@ struct FrameBlockRef {
 struct FrameRef {
     uint32_t first_block, nblocks;
     bool has_size, has_checksum, closed;
+    bool linked = false;      // BlockMode::Linked: blocks may reference the frame's earlier output
     uint64_t content_size;
     uint32_t content_checksum;
 };
@@ -1160,7 +1378,7 @@ lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, siz
             if (flg & 0x01) o += 4;
             if ((uint8_t)(lz4b200_xxh32(in + h, o - h, 0) >> 8) != in[o]) { walk_err = LZ4B200_FRAME_HEADER_CHECKSUM; break; }
             if (flg & 0x01) { walk_err = LZ4B200_FRAME_DICTIONARY; break; }
-            if (!(flg & 0x20)) { walk_err = LZ4B200_FRAME_LINKED_UNSUPPORTED; break; }
+            fr.linked = !(flg & 0x20);
             ip = o + 1;
         }
         const uint32_t fidx = (uint32_t)frames.size();
@@ -1225,7 +1443,38 @@ lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, siz
         CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pick.p, h_pick.data(), nb, cudaMemcpyHostToDevice, s));
         BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_slots.p, ctx->d_out_off.p,
                     ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
-        lz4b200_status st = launch_decompress(ctx, a, s);
+        bool any_linked = false;
+        for (const FrameRef &fr : frames) any_linked |= fr.linked && fr.nblocks > 1;
+        lz4b200_status st;
+        if (any_linked) {
+            // BlockMode::Linked (frame/decompress.rs:196-222): the blocks of a frame form a dependency chain; the
+            // linked kernel resolves offsets that reach before a block in the outputs of its predecessors
+            std::vector<uint32_t> h_first(nb), h_slen(nb);
+            std::vector<uint64_t> h_soff(nb);
+            for (uint32_t b = 0; b < nb; b++) {
+                const FrameRef &fr = frames[blocks[b].frame_idx];
+                h_first[b] = fr.linked ? fr.first_block : b;
+                h_slen[b] = blocks[b].stored ? blocks[b].payload_len : 0;
+                h_soff[b] = blocks[b].payload_off;
+                // a stored block of zero length would read as "compressed": give it no work and no history instead
+                if (blocks[b].stored && blocks[b].payload_len == 0) { h_slen[b] = 0; h_in_len[b] = 0; }
+            }
+            CTX_CUDA(ctx, ctx->d_link_first.reserve(nb)); CTX_CUDA(ctx, ctx->d_stored_len.reserve(nb));
+            CTX_CUDA(ctx, ctx->d_stored_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_done.reserve(nb));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_link_first.p, h_first.data(), nb * 4, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_len.p, h_slen.data(), nb * 4, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_off.p, h_soff.data(), nb * 8, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemsetAsync(ctx->d_done.p, 0, nb * 4, s));
+            CTX_CUDA(ctx, cudaStreamSynchronize(s));         // h_first & co. are locals
+            a.link_first = ctx->d_link_first.p; a.stored_off = ctx->d_stored_off.p;
+            a.stored_len = ctx->d_stored_len.p; a.done = ctx->d_done.p;
+            a.tickets = ctx->d_tickets;
+            const uint32_t grid = std::min<uint32_t>((nb + 3) / 4, (uint32_t)ctx->sm_count * 8);
+            lz4_decompress_blocks_linked<32><<<grid, 128, 0, s>>>(a);
+            st = ctx->check(cudaGetLastError(), "linked decode launch") ? LZ4B200_OK : LZ4B200_CUDA_ERROR;
+        } else {
+            st = launch_decompress(ctx, a, s);
+        }
         if (st != LZ4B200_OK) return st;
         CTX_CUDA(ctx, cudaMemcpyAsync(produced.data(), ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
         CTX_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));

@@ -9,19 +9,33 @@
 //   matcher warp : owns the 4096-slot table in shared memory and runs the exact emulation of the sequential
 //                  probe loop (32 probes per batch, in-batch table forwarding with match.any); it pushes one
 //                  16-byte tuple per sequence into a shared-memory ring and goes straight on to the next probe.
-//   emitter warp : takes 32 tuples at a time, one per lane; every lane sizes its own sequence, a warp
+//   emitter warp : takes a batch of tuples at a time, one per lane; every lane sizes its own sequence, a warp
 //                  exclusive scan (__shfl_up) turns sizes into output offsets, and the lanes write token /
 //                  length bytes / literals / offset of 32 sequences at once (long literal runs are copied by the
 //                  whole warp).  This is the scan-compacted emission the north star asks for, and it takes
 //                  ~27 % of the per-sequence chain off the matcher.
 //
-// Hand-off: two halves of 32 tuples, mbarriers "full[h]" / "empty[h]" per pair in shared memory — the matcher
+// Hand-off: two halves of 16 tuples, mbarriers "full[h]" / "empty[h]" per pair in shared memory — the matcher
 // never waits unless the emitter is two batches behind.
 #pragma once
+#ifndef ENC_FASTW
+#define ENC_FASTW 1     // 1: settle slot collisions of the first <= 4 probes with shuffles instead of match.any
+#endif
+#ifndef ENC_RI_PATCH
+#define ENC_RI_PATCH 0  // 1: re-insert folded into the batch commit (no store->load dependency); 0: store + syncwarp first
+#endif
+#ifndef ENC_EMIT_SLEEP_NS
+#define ENC_EMIT_SLEEP_NS 1000   // emitter back-off while its queue is empty (0: spin)
+#endif
+#ifndef ENC_WINDOW
+#define ENC_WINDOW 0   // 1: first probe batch reads a cp.async-filled shared-memory ring (measured: 20.6 vs 20.1 ms without)
+#endif
 
 namespace lz4b200 {
 
-constexpr uint32_t kSeqBatchEntries = 32;
+constexpr uint32_t kSeqBatchEntries = 16;      // tuples per hand-off (two halves per pair)
+constexpr uint32_t kWinBytes = 512;            // input look-ahead ring per pair: 4 lines of 128 bytes
+constexpr uint32_t kRingBytes = ENC_WINDOW ? kWinBytes : 0;   // shared memory actually reserved for it
 constexpr uint32_t kExitBlock = 0xffffffffu;
 constexpr uint32_t kSmallLit = 24;            // literal runs up to this length are copied by the owning lane
 
@@ -44,6 +58,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
+}
+// Consumer-side wait: the emitter is idle most of the time; spinning on try_wait would burn issue slots the
+// matchers need, so it backs off between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_addr(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(4u * ENC_EMIT_SLEEP_NS) : "memory");
+        if (done) break;
+#if ENC_EMIT_SLEEP_NS
+        __nanosleep(ENC_EMIT_SLEEP_NS);
+#endif
+    }
 }
 
 // Producer side of the tuple ring (all state is warp-uniform).
@@ -86,11 +115,88 @@ struct SeqProducer {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Input look-ahead window.  With 24 tables resident per SM the L1 is down to its 28 KB floor, so every
+// global load is an L2 round trip (several hundred cycles under load) and the probe loop would pay one per
+// sequence just to read the bytes at the cursor.  Instead the matcher keeps the four 128-byte lines
+// [c-1, c+3) around the cursor (c = line of the cursor) in a shared-memory ring, filled by asynchronous
+// global->shared copies (cp.async, 16 bytes per lane, L2-only) that are issued two lines ahead of their
+// first use.  The first probe batch (32 probes, <= 40 bytes), the re-insert of cur-2 and the input side of
+// the first forward-extension round read the ring (29-cycle LDS); only the candidate side goes to L2.
+// Positions are kept in "x space": x = position + (src & 127), so ring lines are 128-byte aligned in memory
+// and every 16-byte copy is aligned.  Copies are clipped to the block: a chunk that ends before the block or
+// starts after it reads nothing (src-size 0 = zero fill), the last chunk reads only the block's bytes.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g, uint32_t bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct InputWindow {
+    const uint32_t *ring;     // kWinBytes / 4 words
+    uint32_t ring_s;          // shared-space address of the ring
+    const uint8_t *src_al;    // src rounded down to 128 bytes
+    uint32_t mis;             // src - src_al
+    uint32_t xend;            // mis + n
+    uint32_t nlines;          // lines that contain block bytes
+    uint32_t hi;              // lines below hi have been requested
+    uint32_t ready;           // lines below ready have landed
+
+    __device__ __forceinline__ void init(const uint8_t *src, uint32_t n, uint32_t *ring_)
+    {
+        ring = ring_;
+        ring_s = smem_addr(ring_);
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 127u);
+        src_al = src - mis;
+        xend = mis + n;
+        nlines = (xend + 127u) >> 7;
+        hi = 0; ready = 0;
+    }
+    // Request the lines of [c-1, c+3) that are not resident yet and make sure those needed now have landed.
+    __device__ __forceinline__ void advance(uint32_t xc, uint32_t lane)
+    {
+        const uint32_t c = xc >> 7;
+        const uint32_t want = min(c + 3u, nlines);
+        if (hi < want) {
+            const uint32_t first = max(hi, c ? c - 1u : 0u);
+            const uint32_t line = first + (lane >> 3);
+            if (line < want) {
+                const uint32_t xo = line * 128u + (lane & 7u) * 16u;
+                uint32_t bytes = 0;
+                if (xo + 16u > mis && xo < xend) bytes = min(16u, xend - xo);
+                cp_async16(ring_s + (xo & (kWinBytes - 1u)), src_al + xo, bytes);
+            }
+            cp_async_commit();
+            hi = want;
+        }
+        const uint32_t need = min(((xc + 71u) >> 7) + 1u, hi);   // first batch + first extension round: < 72 bytes ahead
+        if (ready < need) {
+            cp_async_wait_all();
+            __syncwarp();
+            ready = hi;
+        }
+    }
+    // low 5 bytes at x (ring must hold the line(s)): (lo32, hi8)
+    __device__ __forceinline__ void ro5(uint32_t x, uint32_t &lo, uint32_t &hi8) const
+    {
+        const uint32_t a = ring[(x >> 2) & (kWinBytes / 4 - 1u)], b = ring[((x >> 2) + 1u) & (kWinBytes / 4 - 1u)];
+        const uint32_t sh = (x & 3u) * 8u;
+        lo = __funnelshift_r(a, b, sh);
+        hi8 = (b >> sh) & 0xffu;
+    }
+    __device__ __forceinline__ uint8_t byte(uint32_t x) const
+    {
+        return reinterpret_cast<const uint8_t *>(ring)[x & (kWinBytes - 1u)];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // matcher: the search half of compress_internal.  Table semantics identical to encode_block_v1.
 // ---------------------------------------------------------------------------------------------
 template <typename TabT>
-__device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, bool cont, bool h5,
-                                            SeqProducer &pr, uint32_t lane)
+__device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, uint32_t *ring,
+                                            bool cont, bool h5, SeqProducer &pr, uint32_t lane)
 {
     constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -107,6 +213,8 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         __syncwarp();
     }
     const WordView view(src);
+    InputWindow win;
+    win.init(src, n, ring);
     const uint32_t last_probe = n - 12;
     const uint32_t lim = n - 6;                                 // matches end before the last END_OFFSET bytes
     uint32_t anchor = 0, cur = 0;
@@ -120,30 +228,71 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
     }
 
     for (;;) {                                                  // one sequence per iteration
-        if (lane < 2) prefetch_l1(src + min(cur + 192u + 128u * lane, n - 1u));
+#if ENC_WINDOW
+        win.advance(cur + win.mis, lane);
+#endif
         uint32_t base = cur, stride = 1, cand, mpos;
+        bool in_win = ENC_WINDOW != 0;                          // first batch: probe bytes come from the ring
         for (;;) {                                              // probe batches: compress.rs:373-439
             const uint32_t p = base + lane * stride;
             const bool term = p > last_probe;
             uint32_t v4, hi;
-            view.ro5(term ? 0u : p, v4, hi);
+            if (in_win) win.ro5(p + win.mis, v4, hi);           // term lanes read ring bytes they never use
+            else view.ro5(term ? 0u : p, v4, hi);
+            uint32_t s2 = 0xffffffffu;
             if (ri) {
-                // the re-insert of the previous sequence rides along with the first probe loads
-                uint32_t lo2, hi2; view.ro5(cur - 2u, lo2, hi2);
-                const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+                // The re-insert of the previous sequence (compress.rs:460-461) rides along with the first probe loads.
+                uint32_t lo2, hi2;
+                if (ENC_WINDOW) win.ro5(cur - 2u + win.mis, lo2, hi2); else view.ro5(cur - 2u, lo2, hi2);
+                s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+#if !ENC_RI_PATCH
                 if (lane == 0) tab[s2] = (TabT)(cur - 2u);
                 __syncwarp();
+                s2 = 0xffffffffu;
+#endif
                 ri = false;
             }
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
             uint32_t cnd = kInvalid;
             if (!term) cnd = tab[key]; else key = 0x10000u | lane;
-            const uint32_t same = __match_any_sync(kFull, key);
-            const uint32_t prior = same & lt_mask;
-            if (prior) cnd = base + (31u - __clz(prior)) * stride;   // forwarded in-batch write
-            const bool chk = !term && cnd != kInvalid && p - cnd <= 65535u;
-            const bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
-            const uint32_t hits = __ballot_sync(kFull, hit), terms = __ballot_sync(kFull, term);
+#if ENC_RI_PATCH
+            // Nothing waits for the re-insert's table write: a probe on the same slot takes cur-2 directly and the
+            // write itself is made with this batch's commits (dropped if a committed probe overwrites the slot).
+            if (key == s2) cnd = cur - 2u;
+#endif
+            // The sequential loop overwrites T[h] before the next probe, so a probe sees the write of an earlier probe
+            // of this batch when their slots collide.  First check the table's pre-batch candidates speculatively:
+            // if none of the probes up to the first speculative hit w0 shares its slot with an earlier probe, the
+            // speculation was exact.  For w0 <= 3 (89 % of JSON sequences) that is settled with three shuffles;
+            // match.any — whose latency grows with the number of distinct keys, ~900 cycles for 32 — only runs
+            // for the rest.
+            bool chk = !term && cnd != kInvalid && p - cnd <= 65535u;
+            bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+            uint32_t hits = __ballot_sync(kFull, hit);
+            const uint32_t terms = __ballot_sync(kFull, term);
+            const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+            uint32_t same = 1u << lane;                         // lanes of this batch on my slot (incl. me)
+            bool exact = w0 == 0u;
+#if ENC_FASTW
+            if (w0 >= 1u && w0 <= 3u) {
+                const uint32_t k0 = __shfl_sync(kFull, key, 0), k1 = __shfl_sync(kFull, key, 1), k2 = __shfl_sync(kFull, key, 2);
+                const bool clash = (lane >= 1u && key == k0) || (lane >= 2u && key == k1) || (lane >= 3u && key == k2);
+                exact = (__ballot_sync(kFull, clash && lane <= w0) == 0u);
+            }
+#endif
+            if (!exact) {
+                same = __match_any_sync(kFull, key);
+                const uint32_t prior = same & lt_mask;
+                const uint32_t le0 = w0 >= 31u ? kFull : ((2u << w0) - 1u);
+                if (__ballot_sync(kFull, prior != 0u) & le0) {
+                    if (prior) {
+                        cnd = base + (31u - __clz(prior)) * stride;          // forwarded in-batch write
+                        chk = p - cnd <= 65535u;                             // lanes with a prior are never term lanes
+                        hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+                    }
+                    hits = __ballot_sync(kFull, hit);
+                }
+            }
             const uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
             const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
             if (tfirst < win) {                                 // compress.rs:381-384: the rest is literals
@@ -155,14 +304,21 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
             if (lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
+#if ENC_RI_PATCH
+            if (s2 != 0xffffffffu) {                            // uniform: first batch after a match
+                const uint32_t dups = __ballot_sync(kFull, key == s2 && lane <= upto);
+                if (lane == 0 && dups == 0u) tab[s2] = (TabT)(cur - 2u);
+            }
+#endif
             __syncwarp();
             if (win < 32u) {
-                mpos = __shfl_sync(kFull, p, win);
+                mpos = base + win * stride;
                 cand = __shfl_sync(kFull, cnd, win);
                 break;
             }
             base += 32u * stride;
             stride++;
+            in_win = false;
         }
         const uint32_t dist = mpos - cand;
 
@@ -170,7 +326,8 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         const uint32_t room = min(cand, mpos - anchor);         // how far both sides may step back (0 for literal-free sequences)
         const uint32_t qf = mpos + 4u + lane;
         const bool inf = qf < lim;
-        const uint8_t f1 = __ldg(src + (inf ? qf : mpos)), f2 = __ldg(src + (inf ? qf : mpos) - dist);
+        const uint8_t f1 = in_win ? win.byte(qf + win.mis) : __ldg(src + (inf ? qf : mpos));
+        const uint8_t f2 = __ldg(src + (inf ? qf : mpos) - dist);
         uint32_t kb = 0;
         if (room) {                                             // compress.rs:272-287
             const bool inb = lane < room;
@@ -219,6 +376,120 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// matcher with an external dictionary: compress_into_with_dict (compress.rs:554-583, 610-616).
+// The dictionary logically precedes the input: the table holds STREAM positions (input position + dictionary
+// length), init_dict seeds it with every third dictionary position, and a candidate below the dictionary
+// length is matched against the dictionary's bytes (compress.rs:412-421) — backwards to its first byte,
+// forwards to its last (a match never runs from the dictionary into the input).  This path is about
+// completeness, not speed: plain global loads, full match.any per batch.
+// ---------------------------------------------------------------------------------------------
+template <typename TabT>
+__device__ __forceinline__ void match_block_dict(const uint8_t *__restrict__ src, uint32_t n,
+                                                 const uint8_t *__restrict__ dict, uint32_t dlen, TabT *tab, bool h5,
+                                                 SeqProducer &pr, uint32_t lane)
+{
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t off = dlen;                                  // input_stream_offset
+    if (n < 13) {                                               // compress.rs:343-346
+        pr.push_final(0, n, lane);
+        return;
+    }
+    {
+        constexpr uint32_t words = 4096 * sizeof(TabT) / 16;
+        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
+        for (uint32_t i = lane; i < words; i += 32) t128[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+    }
+    const WordView view(src), dview(dict);
+    // init_dict (compress.rs:571-583): positions 0, 3, 6, ... with 8 readable bytes, in order; the last writer of
+    // a slot wins, within a batch of 32 that is the highest lane
+    for (uint32_t i0 = 0; i0 + 8u <= dlen; i0 += 96u) {
+        const uint32_t i = i0 + 3u * lane;
+        const bool act = i + 8u <= dlen;
+        uint32_t lo, hi; dview.ro5(act ? i : 0u, lo, hi);
+        const uint32_t key = act ? (h5 ? slot_h5(lo, hi) : slot_h4(lo)) : (0x10000u | lane);
+        const uint32_t same = __match_any_sync(kFull, key);
+        if (act && (31u - __clz(same)) == lane) tab[key] = (TabT)i;
+        __syncwarp();
+    }
+    const uint32_t last_probe = n - 12;
+    const uint32_t lim = n - 6;
+    uint32_t anchor = 0, cur = 0;
+    bool ri = false;
+    for (;;) {                                                  // one sequence per iteration
+        uint32_t base = cur, stride = 1, cand_s, mpos;
+        for (;;) {                                              // probe batches: compress.rs:373-439
+            const uint32_t p = base + lane * stride;
+            const bool term = p > last_probe;
+            uint32_t v4, hi;
+            view.ro5(term ? 0u : p, v4, hi);
+            if (ri) {                                           // compress.rs:460-461
+                uint32_t lo2, hi2; view.ro5(cur - 2u, lo2, hi2);
+                const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+                if (lane == 0) tab[s2] = (TabT)(cur - 2u + off);
+                __syncwarp();
+                ri = false;
+            }
+            uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
+            uint32_t cnd = 0;                                   // stream position of the candidate
+            if (!term) cnd = tab[key]; else key = 0x10000u | lane;
+            const uint32_t same = __match_any_sync(kFull, key);
+            const uint32_t prior = same & lt_mask;
+            if (prior) cnd = off + base + (31u - __clz(prior)) * stride;   // forwarded in-batch write
+            const bool chk = !term && p + off - cnd <= 65535u;
+            const bool in_dict = cnd < off;
+            const uint32_t c4 = in_dict ? dview.ro4s(chk ? cnd : 0u) : view.ro4(chk ? cnd - off : 0u);
+            const bool hit = chk & (c4 == v4);
+            const uint32_t hits = __ballot_sync(kFull, hit), terms = __ballot_sync(kFull, term);
+            const uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
+            if (tfirst < win) {                                 // compress.rs:381-384
+                pr.push_final(anchor, n, lane);
+                return;
+            }
+            const uint32_t upto = win < 32u ? win : 31u;
+            const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
+            const uint32_t mine = same & le_mask;
+            if (lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)(p + off);
+            __syncwarp();
+            if (win < 32u) {
+                mpos = base + win * stride;
+                cand_s = __shfl_sync(kFull, cnd, win);
+                break;
+            }
+            base += 32u * stride;
+            stride++;
+        }
+        const uint32_t dist = mpos + off - cand_s;
+        const bool cd = cand_s < off;                           // candidate lives in the dictionary
+        const uint8_t *__restrict__ cs = cd ? dict : src;
+        const uint32_t clen = cd ? dlen : n;
+        uint32_t ci = cd ? cand_s : cand_s - off;               // its index in its own buffer
+        for (;;) {                                              // backwards: compress.rs:272-287
+            const uint32_t room = min(ci, mpos - anchor);
+            const bool ok = lane < room && __ldg(src + mpos - (lane < room ? 1u + lane : 0u)) == __ldg(cs + ci - (lane < room ? 1u + lane : 0u));
+            const uint32_t bad = ~__ballot_sync(kFull, ok);
+            const uint32_t kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+            mpos -= kb; ci -= kb;
+            if (kb < 32u) break;
+        }
+        uint32_t end = mpos + 4u, cj = ci + 4u;
+        for (;;) {                                              // forwards: compress.rs:156-216 (input and source limits)
+            const uint32_t q = end + lane, cq = cj + lane;
+            const bool in = q < lim && cq < clen;
+            const bool ok = in && __ldg(src + (in ? q : mpos)) == __ldg(cs + (in ? cq : ci));
+            const uint32_t bad = ~__ballot_sync(kFull, ok);
+            const uint32_t k = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+            end += k; cj += k;
+            if (k < 32u) break;
+        }
+        pr.push(anchor, mpos, dist, end, lane);
+        anchor = cur = end;
+        ri = true;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // emitter: compress.rs:463-486 for 32 sequences at a time.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint8_t *put_len_ext(uint8_t *p, uint32_t v)     // v = length - 15 (write_integer, compress.rs:217-242)
@@ -236,7 +507,7 @@ __device__ __forceinline__ void emit_loop(const BatchArgs &a, const uint4 *q, co
     uint32_t o = 0;
     for (uint32_t j = 0;; j++) {
         const uint32_t h = j & 1u;
-        mbar_wait(bars + h, (j >> 1) & 1u);
+        mbar_wait_relaxed(bars + h, (j >> 1) & 1u);
         const uint32_t b = meta[h * 4 + 0], cnt = meta[h * 4 + 1], fl = meta[h * 4 + 2];
         uint4 e = make_uint4(0, 0, 0, 0);
         if (lane < cnt && b != kExitBlock) e = q[h * kSeqBatchEntries + lane];
@@ -298,19 +569,29 @@ __device__ __forceinline__ void emit_loop(const BatchArgs &a, const uint4 *q, co
 }
 
 // One CTA = kPairs matcher warps (warps 0..kPairs-1) + kPairs emitter warps.  Shared memory per pair: the
-// table (8 KiB for blocks <= 64 KiB, 16 KiB above), 1 KiB of tuples, 32 bytes of batch headers, 4 mbarriers.
+// table (8 KiB for blocks <= 64 KiB, 16 KiB above), 512 bytes of tuples, the 512-byte input ring, 32 bytes of
+// batch headers, 4 mbarriers.
 template <typename TabT, int kPairs>
-__global__ void __launch_bounds__(kPairs * 64)
+constexpr int split_ctas_per_sm()                              // what 227 KB of shared memory (1 KB reserved per CTA) holds
+{
+    return (int)((227u * 1024u) / (kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + kRingBytes + 64) + 1024u));
+}
+
+template <typename TabT, int kPairs, bool kDict>
+__global__ void __launch_bounds__(kPairs * 64, split_ctas_per_sm<TabT, kPairs>())
 lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t pair = warp < (uint32_t)kPairs ? warp : warp - kPairs;
     TabT *tab = reinterpret_cast<TabT *>(smem_raw) + pair * 4096;
-    uint4 *q = reinterpret_cast<uint4 *>(smem_raw + kPairs * 4096 * sizeof(TabT)) + pair * 2 * kSeqBatchEntries;
-    uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16)) + pair * 8;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + 32)) + pair * 4;
-    if (threadIdx.x < (uint32_t)kPairs * 4u) mbar_init(reinterpret_cast<uint64_t *>(smem_raw + kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + 32)) + threadIdx.x, 1u);
+    constexpr size_t kTab = 4096 * sizeof(TabT), kQ = 2 * kSeqBatchEntries * 16;
+    uint4 *q = reinterpret_cast<uint4 *>(smem_raw + kPairs * kTab) + pair * 2 * kSeqBatchEntries;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(smem_raw + kPairs * (kTab + kQ)) + pair * (kRingBytes / 4);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + kPairs * (kTab + kQ + kRingBytes)) + pair * 8;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kPairs * (kTab + kQ + kRingBytes + 32)) + pair * 4;
+    if (threadIdx.x < (uint32_t)kPairs * 4u)
+        mbar_init(reinterpret_cast<uint64_t *>(smem_raw + kPairs * (kTab + kQ + kRingBytes + 32)) + threadIdx.x, 1u);
     __syncthreads();
     if (warp >= (uint32_t)kPairs) {
         emit_loop(a, q, meta, bars, lane);
@@ -320,15 +601,19 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
     SeqProducer pr{q, meta, bars, 0u, 0u, 0u, 0u};
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
-        if ((n <= 65536u) != kSmall) continue;
+        const uint64_t span = (uint64_t)n + (kDict ? a.dict_len : 0u);      // table layout follows dict + input: compress.rs:559
+        if ((span <= 65536u) != kSmall) continue;
         const uint32_t fl = a.flags ? a.flags[b] : 0u;
         if ((uint64_t)a.out_cap[b] < max_output_size_dev(n)) {              // compress.rs:338-340
             if (lane == 0) { a.out_len[b] = 0; a.status[b] = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; }
             continue;
         }
-        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;   // compress.rs:559
+        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || span >= 65535u;
         pr.block = b; pr.first = 1;
-        match_block<TabT>(a.in + a.in_off[b], n, tab, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
+        if constexpr (kDict)
+            match_block_dict<TabT>(a.in + a.in_off[b], n, a.dict, a.dict_len, tab, h5, pr, lane);
+        else
+            match_block<TabT>(a.in + a.in_off[b], n, tab, ring, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
     }
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0, lane);
@@ -336,6 +621,6 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
 }
 
 template <typename TabT, int kPairs>
-constexpr size_t split_smem_bytes() { return (size_t)kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + 32 + 32); }
+constexpr size_t split_smem_bytes() { return (size_t)kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + kRingBytes + 32 + 32); }
 
 }  // namespace lz4b200

@@ -50,6 +50,15 @@ struct BatchArgs {
     uint64_t *err_expected;        // decompress only; may be null
     uint32_t nblocks;
     uint32_t *tickets;             // [0] next block, [1] warps finished (self-resetting)
+    const uint8_t *dict;           // external dictionary shared by every block of the batch (may be null)
+    uint32_t dict_len;             // <= 65536: callers keep only the last WINDOW_SIZE bytes
+    // BlockMode::Linked frames (lz4_decompress_blocks_linked only): block b may reference the output of the blocks
+    // [link_first[b], b) of its frame.  Stored (uncompressed) blocks are not decoded; their bytes are history at
+    // in + stored_off[k].  done[] is zeroed by the host and set when a block's output is complete.
+    const uint32_t *link_first;
+    const uint64_t *stored_off;
+    const uint32_t *stored_len;
+    uint32_t *done;
 };
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -93,6 +102,13 @@ struct WordView {
     {
         uint32_t x = pos + mis;
         uint32_t a = __ldg(w + (x >> 2)), b = __ldg(w + (x >> 2) + 1);
+        return __funnelshift_r(a, b, (x & 3u) * 8u);
+    }
+    // 4 bytes at pos; requires only pos + 4 <= n (the second word is fetched only when it holds one of the 4 bytes)
+    __device__ __forceinline__ uint32_t ro4s(uint32_t pos) const
+    {
+        uint32_t x = pos + mis;
+        uint32_t a = __ldg(w + (x >> 2)), b = (x & 3u) ? __ldg(w + (x >> 2) + 1) : 0u;
         return __funnelshift_r(a, b, (x & 3u) * 8u);
     }
     // low 5 bytes at pos as (lo32, hi8); requires pos + 8 <= n.
@@ -160,7 +176,8 @@ __device__ __forceinline__ void copy_match(uint8_t *dst, uint32_t dist, uint32_t
 template <int G>
 __device__ __forceinline__ int decode_sequence_checked(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
                                                     uint32_t cap, uint32_t &ip_io, uint32_t &op_io, uint32_t sub,
-                                                    uint32_t gmask, DecResult &r)
+                                                    uint32_t gmask, DecResult &r, const uint8_t *__restrict__ dict = nullptr,
+                                                    uint32_t dlen = 0)
 {
     uint32_t ip = ip_io, op = op_io;
     const uint32_t tok = __ldg(src + ip++);
@@ -195,13 +212,22 @@ __device__ __forceinline__ int decode_sequence_checked(const uint8_t *__restrict
             if (b != 255) break;
         }
     }
-    if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return 2; }                      // :399
+    if (dist > op + dlen) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return 2; }               // :399
     if (mlen > (uint64_t)(cap - op)) {                                                             // :402-406
         r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + mlen; return 2;
     }
+    uint32_t m = (uint32_t)mlen;
+    if (dist > op) {
+        // the match starts in the external dictionary (copy_from_dict, decompress.rs:85-109): its first
+        // dist - op bytes are the dictionary's tail; whatever is left continues at the start of the output
+        const uint32_t from_dict = min(m, dist - op);
+        const uint8_t *d = dict + (dlen + op - dist);
+        for (uint32_t i = sub; i < from_dict; i += G) dst[op + i] = __ldg(d + i);
+        op += from_dict; m -= from_dict;
+    }
     __syncwarp(gmask);                                         // earlier stores of this group -> visible
-    copy_match<G>(dst + op, dist, (uint32_t)mlen, sub, gmask);
-    op += (uint32_t)mlen;
+    if (m) copy_match<G>(dst + op, dist, m, sub, gmask);
+    op += m;
     if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return 2; }                       // :439-443
     ip_io = ip; op_io = op;
     return 0;
@@ -217,7 +243,8 @@ constexpr int kSeqBatch = 4;
 
 template <int G>
 __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                                  uint32_t cap, uint32_t sub, uint32_t gmask)
+                                                  uint32_t cap, uint32_t sub, uint32_t gmask,
+                                                  const uint8_t *__restrict__ dict, uint32_t dlen)
 {
     constexpr int K = kSeqBatch;
     constexpr int LJ = (14 + G - 1) / G;          // byte steps for a literal run of at most 14
@@ -312,7 +339,7 @@ __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ sr
         }
         if (cnt == K) continue;
         // ---- the sequence that stopped the walk: every check, one at a time ---------------------
-        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
+        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r, dict, dlen);
         if (c == 1) break;
         if (c == 2) return r;
     }
@@ -327,7 +354,8 @@ __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ sr
 // walk and literal copy instead of stalling the group at the store (the hottest stall in the profile).
 template <int G>
 __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
-                                                         uint32_t cap, uint32_t sub, uint32_t gmask)
+                                                         uint32_t cap, uint32_t sub, uint32_t gmask,
+                                                         const uint8_t *__restrict__ dict, uint32_t dlen)
 {
     DecResult r{0u, LZ4B200_OK, 0ull};
     if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // decompress.rs:207-209
@@ -365,7 +393,21 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                         op += lit;
                     }
                     if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return r; }
-                    if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }
+                    if (dist > op) {
+                        // the match starts before the output: in the external dictionary (copy_from_dict,
+                        // decompress.rs:85-109), or nowhere (decompress.rs:287-289)
+                        if (dist > op + dlen) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }
+                        FLUSH_PENDING();
+                        const uint32_t from_dict = min(mlen, dist - op);
+                        const uint8_t *d = dict + (dlen + op - dist);
+                        for (uint32_t i = sub; i < from_dict; i += G) dst[op + i] = __ldg(d + i);
+                        op += from_dict;
+                        __syncwarp(gmask);
+                        if (mlen > from_dict) copy_match<G>(dst + op, dist, mlen - from_dict, sub, gmask);
+                        op += mlen - from_dict;
+                        ip = q + adv;
+                        continue;
+                    }
                     FLUSH_PENDING();
                     __syncwarp(gmask);
                     if (kDefer && dist >= mlen && mlen <= 4u * G) {
@@ -385,7 +427,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
             }
         }
         FLUSH_PENDING();
-        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
+        const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r, dict, dlen);
         if (c == 1) break;
         if (c == 2) return r;
     }
@@ -395,9 +437,141 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Linked blocks (frame/decompress.rs:196-222, 277-305).  In BlockMode::Linked a block's matches may reach
+// into the earlier output of its frame (the reference keeps a prefix + ext_dict window of >= 64 KiB; offsets are
+// 16-bit, so "everything the frame has produced so far" is equivalent).  That makes the blocks of one frame a
+// dependency chain: a group decodes its block normally and, the first time an offset reaches before the block,
+// waits for the predecessor blocks it needs (tickets are handed out in stream order, so every predecessor is
+// already resident and running) and reads their bytes through L2.  Frames are independent of each other.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t wait_block_done(const BatchArgs &a, uint32_t k)
+{
+    const uint32_t stored = a.stored_len[k];
+    if (stored) return stored;
+    volatile uint32_t *flag = a.done + k;
+    while (*flag == 0u) __nanosleep(200);
+    __threadfence();
+    return __ldcg(a.out_len + k);
+}
+
+template <int G>
+__device__ __forceinline__ DecResult decode_block_linked(const BatchArgs &a, uint32_t b, uint32_t sub, uint32_t gmask)
+{
+    const uint8_t *__restrict__ src = a.in + a.in_off[b];
+    const uint32_t n = a.in_len[b], cap = a.out_cap[b], first = a.link_first[b];
+    uint8_t *dst = a.out + a.out_off[b];
+    DecResult r{0u, LZ4B200_OK, 0ull};
+    if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // decompress.rs:207-209
+    uint32_t ip = 0, op = 0;
+    for (;;) {
+        const uint32_t tok = __ldg(src + ip++);
+        uint64_t lit = tok >> 4;
+        if (lit == 15) {                                           // read_integer_ptr: decompress.rs:126-157
+            for (;;) {
+                if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }
+                const uint32_t v = __ldg(src + ip++);
+                lit += v;
+                if (v != 255) break;
+            }
+        }
+        if (lit) {
+            if (lit > (uint64_t)(n - ip)) { r.status = LZ4B200_DEC_LITERAL_OUT_OF_BOUNDS; return r; }
+            if (lit > (uint64_t)(cap - op)) {
+                r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + lit; return r;
+            }
+            for (uint32_t i = sub; i < (uint32_t)lit; i += G) dst[op + i] = __ldg(src + ip + i);
+            ip += (uint32_t)lit; op += (uint32_t)lit;
+        }
+        if (ip >= n) break;                                        // the stream ends after literals
+        if (n - ip < 2) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }
+        const uint32_t dist = (uint32_t)__ldg(src + ip) | ((uint32_t)__ldg(src + ip + 1) << 8);
+        ip += 2;
+        if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; return r; }
+        uint64_t mlen = 4u + (tok & 15u);
+        if (mlen == 19) {
+            for (;;) {
+                if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }
+                const uint32_t v = __ldg(src + ip++);
+                mlen += v;
+                if (v != 255) break;
+            }
+        }
+        // locate the match start when it lies before this block: walk back over the frame's earlier blocks
+        uint32_t k = b, back = 0, len_k = 0;
+        if (dist > op) {
+            back = dist - op;
+            bool found = false;
+            while (k > first) {
+                k--;
+                len_k = wait_block_done(a, k);
+                if (back <= len_k) { found = true; break; }
+                back -= len_k;
+            }
+            if (!found) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; return r; }   // decompress.rs:287-289 / :399-401
+        }
+        if (mlen > (uint64_t)(cap - op)) {
+            r.status = LZ4B200_DEC_OUTPUT_TOO_SMALL; r.expected = (uint64_t)op + mlen; return r;
+        }
+        uint32_t m = (uint32_t)mlen;
+        while (m && k < b) {                                       // bytes that come from earlier blocks
+            const uint8_t *base = a.stored_len[k] ? a.in + a.stored_off[k] : a.out + a.out_off[k];
+            const uint32_t c = min(m, back);
+            const uint8_t *from = base + (len_k - back);
+            for (uint32_t i = sub; i < c; i += G) dst[op + i] = __ldcg(from + i);
+            op += c; m -= c;
+            k++;
+            if (k < b) { len_k = wait_block_done(a, k); back = len_k; }
+        }
+        __syncwarp(gmask);
+        if (m) copy_match<G>(dst + op, dist, m, sub, gmask);
+        op += m;
+        if (ip >= n) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; return r; }   // may not end on a match
+    }
+    r.written = op;
+    return r;
+}
+
+template <int G>
+__global__ void __launch_bounds__(4 * 32)
+lz4_decompress_blocks_linked(BatchArgs a)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane & (G - 1), leader = lane & ~uint32_t(G - 1);
+    const uint32_t gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << leader);
+    const uint32_t total_groups = gridDim.x * 4 * (32 / G);
+    for (;;) {
+        uint32_t b = 0;
+        if (sub == 0) b = atomicAdd(&a.tickets[0], 1u);
+        b = __shfl_sync(gmask, b, leader);
+        if (b >= a.nblocks) break;
+        if (a.stored_len[b]) continue;                             // stored block: nothing to decode
+        DecResult r = decode_block_linked<G>(a, b, sub, gmask);
+        __threadfence();                                           // this lane's output bytes -> visible device-wide
+        __syncwarp(gmask);
+        if (sub == 0) {
+            a.out_len[b] = r.status == LZ4B200_OK ? r.written : 0u;
+            a.status[b] = r.status;
+            if (a.err_expected) a.err_expected[b] = r.expected;
+            __threadfence();
+            *(volatile uint32_t *)(a.done + b) = 1u;
+        }
+    }
+    if (sub == 0) {
+        __threadfence();
+        if (atomicAdd(&a.tickets[1], 1u) == total_groups - 1) {
+            a.tickets[0] = 0;
+            a.tickets[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
 constexpr int kDecWarpsPerCta = 4;
 
-template <int G, int kBatched>
+// kDict: the batch has an external dictionary (decompress_into_with_dict); a separate instantiation so that the
+// plain kernel's register allocation is untouched (with the dictionary live ptxas spills in the hot loop: 4.2 -> 7.0 ms).
+template <int G, int kBatched, bool kDict>
 __global__ void __launch_bounds__(kDecWarpsPerCta * 32)
 lz4_decompress_blocks(BatchArgs a)
 {
@@ -411,8 +585,10 @@ lz4_decompress_blocks(BatchArgs a)
         b = __shfl_sync(gmask, b, leader);
         if (b >= a.nblocks) break;
         DecResult r = kBatched
-            ? decode_block<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask)
-            : decode_block_simple<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask);
+            ? decode_block<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask,
+                              kDict ? a.dict : nullptr, kDict ? a.dict_len : 0u)
+            : decode_block_simple<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask,
+                                     kDict ? a.dict : nullptr, kDict ? a.dict_len : 0u);
         if (sub == 0) {
             a.out_len[b] = r.status == LZ4B200_OK ? r.written : 0u;
             a.status[b] = r.status;

@@ -67,6 +67,10 @@ def lib():
         L.lz4o_compress_block.argtypes = [u8p, sz, u8p, sz]
         L.lz4o_compress_block_with_table.restype = i64
         L.lz4o_compress_block_with_table.argtypes = [u8p, sz, u8p, sz, C.c_void_p, C.c_uint64]
+        L.lz4o_compress_block_dict.restype = i64
+        L.lz4o_compress_block_dict.argtypes = [u8p, sz, u8p, sz, u8p, sz]
+        L.lz4o_decompress_block_dict.restype = C.c_int
+        L.lz4o_decompress_block_dict.argtypes = [u8p, sz, u8p, sz, u8p, sz] + [C.POINTER(sz)] * 3
         L.lz4o_compress_prepend_size.restype = i64
         L.lz4o_compress_prepend_size.argtypes = [u8p, sz, u8p, sz]
         L.lz4o_decompress_block.restype = C.c_int
@@ -115,6 +119,26 @@ def compress_into(data, cap: int):
     out = np.empty(max(cap, 1), dtype=np.uint8)
     r = lib().lz4o_compress_block(p, n, out.ctypes.data, cap)
     return None if r < 0 else out[:r].tobytes()
+
+
+def compress_with_dict(data, dict_data) -> bytes:
+    """block::compress_with_dict / compress_into_with_dict: src/block/compress.rs:554-583, 610-616, 685-687."""
+    a, p, n = _buf(data)
+    d, dp, dn = _buf(dict_data)
+    out = np.empty(max_output_size(n), dtype=np.uint8)
+    r = lib().lz4o_compress_block_dict(p, n, dp, dn, out.ctypes.data, out.size)
+    assert r >= 0
+    return out[:r].tobytes()
+
+
+def decompress_with_dict(data, cap: int, dict_data):
+    """block::decompress_into_with_dict (src/block/decompress.rs:462-468).  Returns (status, bytes, expected, actual)."""
+    a, p, n = _buf(data)
+    d, dp, dn = _buf(dict_data)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    w, e1, e2 = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    st = lib().lz4o_decompress_block_dict(p, n, dp, dn, out.ctypes.data, cap, C.byref(w), C.byref(e1), C.byref(e2))
+    return st, out[: w.value].tobytes(), e1.value, e2.value
 
 
 def compress_prepend_size(data) -> bytes:

@@ -54,6 +54,7 @@ static inline void st32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 #define LZ4O_MIN_LENGTH    13u     /* block/mod.rs:61 */
 #define LZ4O_MAX_DISTANCE  65535u  /* block/mod.rs:64 */
 #define LZ4O_SLOTS         4096u
+#define LZ4O_WINDOW        65536u  /* block/mod.rs: WINDOW_SIZE */
 
 /* 12-bit slot of the 4-byte multiplicative hash (u16 table, inputs < 65535 bytes). */
 static inline uint32_t slot4(const uint8_t *p)
@@ -102,23 +103,41 @@ static inline size_t common_prefix(const uint8_t *in, size_t cur, size_t cand, s
     return cur - start;
 }
 
+/* Forward match length against an external source (the dictionary): limited by the input's
+ * n - END_OFFSET and by the end of the source (compress.rs:156-216, max_candidate_match). */
+static inline size_t common_prefix_ext(const uint8_t *in, size_t cur, size_t n, const uint8_t *src, size_t cand,
+                                       size_t srclen)
+{
+    size_t lim = n - LZ4O_END_OFFSET, k = 0;
+    if (cur >= lim) return 0;
+    size_t room = lim - cur;
+    if (srclen - cand < room) room = srclen - cand;
+    while (k < room && in[cur + k] == src[cand + k]) k++;
+    return k;
+}
+
 /*
  * One parse, two table layouts.  TAB_T/SLOT are the only differences between the
  * "small input" (u16 + hash4) and the general (u32 + hash5) encoders.
+ * `off` is input_stream_offset; `dict`/`dlen` the external dictionary that logically precedes the input
+ * (ext_dict of compress_internal, compress.rs:318-489; dlen == 0: USE_DICT = false).
  */
 #define DEFINE_ENCODER(NAME, TAB_T, SLOT)                                                        \
 static int64_t NAME(const uint8_t *in, size_t n, uint8_t *out, size_t cap,                       \
-                    TAB_T *tab, size_t off)                                                      \
+                    TAB_T *tab, size_t off, const uint8_t *dict, size_t dlen)                    \
 {                                                                                                \
     if (cap < lz4o_max_output_size(n)) return -1;            /* CompressError::OutputTooSmall */ \
     uint8_t *op = out;                                                                           \
     if (n < LZ4O_MIN_LENGTH) return put_tail_literals(op, in, 0, n) - out;                       \
     const size_t last_probe = n - LZ4O_MFLIMIT;                                                  \
+    const size_t dict_off = off - dlen;                      /* ext_dict_stream_offset */        \
     size_t anchor = 0, cur = 0;                                                                  \
     if (off == 0) { tab[SLOT(in)] = 0; cur = 1; }   /* a block may not start with a match */     \
     for (;;) {                                                                                   \
         size_t misses = 32, next = cur, cand;                                                    \
         uint32_t dist;                                                                           \
+        const uint8_t *csrc;                                                                     \
+        size_t clen;                                                                             \
         for (;;) {                                                                               \
             size_t step = misses >> 5; misses++;                                                 \
             cur = next; next += step;                                                            \
@@ -127,15 +146,17 @@ static int64_t NAME(const uint8_t *in, size_t n, uint8_t *out, size_t cap,      
             cand = tab[s];                                                                       \
             tab[s] = (TAB_T)(cur + off);                                                         \
             if (off + cur - cand > LZ4O_MAX_DISTANCE) continue;                                  \
-            if (cand < off) continue;             /* entry left by an earlier frame block */     \
             dist = (uint32_t)(off + cur - cand);                                                 \
-            cand -= off;                                                                         \
-            if (ld32(in + cand) == ld32(in + cur)) break;                                        \
+            if (cand >= off) { cand -= off; csrc = in; clen = n; }                               \
+            else if (dlen) { cand -= dict_off; csrc = dict; clen = dlen; }                       \
+            else continue;                        /* entry left by an earlier frame block */     \
+            if (ld32(csrc + cand) == ld32(in + cur)) break;                                      \
         }                                                                                        \
-        while (cand > 0 && cur > anchor && in[cur - 1] == in[cand - 1]) { cur--; cand--; }       \
+        while (cand > 0 && cur > anchor && in[cur - 1] == csrc[cand - 1]) { cur--; cand--; }     \
         size_t lit = cur - anchor;                                                               \
         cur += LZ4O_MINMATCH; cand += LZ4O_MINMATCH;                                             \
-        size_t extra = common_prefix(in, cur, cand, n);                                          \
+        size_t extra = csrc == in ? common_prefix(in, cur, cand, n)                              \
+                                  : common_prefix_ext(in, cur, n, csrc, cand, clen);             \
         cur += extra;                                                                            \
         tab[SLOT(in + cur - 2)] = (TAB_T)(cur - 2 + off);                                        \
         *op++ = (uint8_t)(((lit < 15 ? lit : 15) << 4) | (extra < 15 ? extra : 15));             \
@@ -155,10 +176,10 @@ int64_t lz4o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t ca
     if (n < 65535) {
         uint16_t tab[LZ4O_SLOTS];
         memset(tab, 0, sizeof tab);
-        return encode_u16_h4(in, n, out, cap, tab, 0);
+        return encode_u16_h4(in, n, out, cap, tab, 0, NULL, 0);
     } else {
         uint32_t *tab = (uint32_t *)calloc(LZ4O_SLOTS, sizeof(uint32_t));
-        int64_t r = encode_u32_h5(in, n, out, cap, tab, 0);
+        int64_t r = encode_u32_h5(in, n, out, cap, tab, 0, NULL, 0);
         free(tab);
         return r;
     }
@@ -167,7 +188,30 @@ int64_t lz4o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t ca
 int64_t lz4o_compress_block_with_table(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                                        uint32_t *table4096, uint64_t stream_offset)
 {
-    return encode_u32_h5(in, n, out, cap, table4096, (size_t)stream_offset);
+    return encode_u32_h5(in, n, out, cap, table4096, (size_t)stream_offset, NULL, 0);
+}
+
+/* compress_into_with_dict (compress.rs:554-583, 610-616): the dictionary is cut to its last 64 KiB, every third
+ * position with 8 readable bytes is put into the table (init_dict), the table layout follows dict + input length,
+ * and the input is parsed at stream offset = dictionary length.  Dictionaries of <= 3 bytes are dropped
+ * (compress_into_vec_with_dict, compress.rs:626-628; the slice API would read past a shorter one). */
+int64_t lz4o_compress_block_dict(const uint8_t *in, size_t n, const uint8_t *dict, size_t dlen, uint8_t *out,
+                                 size_t cap)
+{
+    if (dlen <= 3) { dict = NULL; dlen = 0; }
+    if (dlen > LZ4O_WINDOW) { dict += dlen - LZ4O_WINDOW; dlen = LZ4O_WINDOW; }
+    if (dlen + n < 65535) {
+        uint16_t tab[LZ4O_SLOTS];
+        memset(tab, 0, sizeof tab);
+        for (size_t i = 0; i + 8 <= dlen; i += 3) tab[slot4(dict + i)] = (uint16_t)i;
+        return encode_u16_h4(in, n, out, cap, tab, dlen, dict, dlen);
+    } else {
+        uint32_t *tab = (uint32_t *)calloc(LZ4O_SLOTS, sizeof(uint32_t));
+        for (size_t i = 0; i + 8 <= dlen; i += 3) tab[slot5(dict + i)] = (uint32_t)i;
+        int64_t r = encode_u32_h5(in, n, out, cap, tab, dlen, dict, dlen);
+        free(tab);
+        return r;
+    }
 }
 
 int64_t lz4o_compress_prepend_size(const uint8_t *in, size_t n, uint8_t *out, size_t cap)
@@ -192,8 +236,18 @@ static inline int get_ext(const uint8_t *in, size_t n, size_t *ip, size_t *len)
     }
 }
 
-int lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
-                          size_t *written, size_t *err_expected, size_t *err_actual)
+/* out[op .. op+mlen) = the bytes `dist` back in the virtual buffer [dict | out] (copy_from_dict + duplicate,
+ * decompress.rs:85-109, 292-301, 410-427): byte-serial LZ77 semantics across the dictionary/output seam. */
+static inline void copy_match_dict(uint8_t *out, size_t op, size_t dist, size_t mlen, const uint8_t *dict, size_t dlen)
+{
+    for (size_t i = 0; i < mlen; i++) {
+        size_t at = op + i;
+        out[at] = at >= dist ? out[at - dist] : dict[dlen + at - dist];
+    }
+}
+
+int lz4o_decompress_block_dict(const uint8_t *in, size_t n, const uint8_t *dict, size_t dlen, uint8_t *out,
+                               size_t cap, size_t *written, size_t *err_expected, size_t *err_actual)
 {
     size_t ip = 0, op = 0;
     *written = 0;
@@ -210,8 +264,9 @@ int lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
             size_t dist = (size_t)in[ip] | ((size_t)in[ip + 1] << 8);
             ip += 2;
             if (dist == 0) return LZ4O_ERR_OFFSET_ZERO;
-            if (dist > op) return LZ4O_ERR_OFFSET_OOB;
-            if (dist >= 18) memcpy(out + op, out + op - dist, 18);
+            if (dist > op + dlen) return LZ4O_ERR_OFFSET_OOB;
+            if (dist > op) copy_match_dict(out, op, dist, mlen, dict, dlen);
+            else if (dist >= 18) memcpy(out + op, out + op - dist, 18);
             else for (size_t i = 0; i < mlen; i++) out[op + i] = out[op - dist + i];
             op += mlen;
             continue;
@@ -233,12 +288,14 @@ int lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
         ip += 2;
         if (dist == 0) return LZ4O_ERR_OFFSET_ZERO;
         if (mlen == 19 && get_ext(in, n, &ip, &mlen)) return LZ4O_ERR_EXPECTED_ANOTHER_BYTE;
-        if (dist > op) return LZ4O_ERR_OFFSET_OOB;
+        if (dist > op + dlen) return LZ4O_ERR_OFFSET_OOB;
         if (mlen > cap - op) {
             *err_expected = op + mlen; *err_actual = cap;
             return LZ4O_ERR_OUTPUT_TOO_SMALL;
         }
-        if (dist >= mlen) {
+        if (dist > op) {
+            copy_match_dict(out, op, dist, mlen, dict, dlen);
+        } else if (dist >= mlen) {
             memcpy(out + op, out + op - dist, mlen);
         } else if (dist == 1) {
             memset(out + op, out[op - 1], mlen);
@@ -250,6 +307,12 @@ int lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
     }
     *written = op;
     return LZ4O_OK;
+}
+
+int lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                          size_t *written, size_t *err_expected, size_t *err_actual)
+{
+    return lz4o_decompress_block_dict(in, n, NULL, 0, out, cap, written, err_expected, err_actual);
 }
 
 int lz4o_decompress_size_prepended(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
@@ -411,7 +474,7 @@ int64_t lz4o_frame_compress(const uint8_t *in, size_t n, int block_size_id, unsi
             for (unsigned i = 0; i < LZ4O_SLOTS; i++) tab[i] = tab[i] > off ? tab[i] - (uint32_t)off : 0;
             off = 0;
         }
-        int64_t c = encode_u32_h5(in + pos, len, scratch, lz4o_max_output_size(len), tab, off);
+        int64_t c = encode_u32_h5(in + pos, len, scratch, lz4o_max_output_size(len), tab, off, NULL, 0);
         const uint8_t *payload; uint32_t info;
         if ((size_t)c < len) { payload = scratch; info = (uint32_t)c; }
         else { payload = in + pos; info = (uint32_t)len | 0x80000000u; c = (int64_t)len; }
@@ -458,9 +521,14 @@ int lz4o_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
             if (flg & 0x01) o += 4;
             if ((uint8_t)(lz4o_xxh32(in + h, o - h, 0) >> 8) != in[o]) return LZ4O_FERR_HEADER_CHECKSUM;
             if (flg & 0x01) return LZ4O_FERR_DICTIONARY;
-            if (!(flg & 0x20)) return LZ4O_FERR_LINKED_UNSUPPORTED;   /* oracle scope: independent */
             ip = o + 1;
         }
+        /* BlockMode::Linked (frame/decompress.rs:196-222, 277-305): a block may reference the frame's earlier
+         * output.  The reference keeps a prefix + ext_dict window of at least WINDOW_SIZE bytes (all of the
+         * frame's output while that is shorter), and offsets are 16-bit, so a block sees exactly
+         * "everything this frame has produced so far" as its dictionary. */
+        const int linked = !(flg & 0x20);
+        const size_t frame_begin = op;
         xxh32_state content; xs_init(&content, 0);
         uint64_t got = 0;
         for (;;) {
@@ -491,7 +559,9 @@ int lz4o_frame_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                 memcpy(out + op, payload, len); produced = len;
             } else {
                 size_t room = cap - op < bs ? cap - op : bs, e1, e2;
-                int st = lz4o_decompress_block(payload, len, out + op, room, &produced, &e1, &e2);
+                int st = linked ? lz4o_decompress_block_dict(payload, len, out + frame_begin, op - frame_begin, out + op,
+                                                             room, &produced, &e1, &e2)
+                                : lz4o_decompress_block(payload, len, out + op, room, &produced, &e1, &e2);
                 if (st != LZ4O_OK) {
                     if (st == LZ4O_ERR_OUTPUT_TOO_SMALL && room < bs) return LZ4O_FERR_OUTPUT_FULL;
                     *block_err = st; return LZ4O_FERR_DECOMPRESSION;
@@ -534,7 +604,7 @@ static void *batch_worker(void *arg)
                 r = lz4o_compress_block(src, j->in_len[b], dst, j->out_cap[b]);
             } else {
                 memset(tab32, 0, LZ4O_SLOTS * sizeof(uint32_t));
-                r = encode_u32_h5(src, j->in_len[b], dst, j->out_cap[b], tab32, 0);
+                r = encode_u32_h5(src, j->in_len[b], dst, j->out_cap[b], tab32, 0, NULL, 0);
             }
             j->status[b] = r < 0 ? LZ4O_ERR_COMPRESS_OUTPUT_TOO_SMALL : LZ4O_OK;
             j->out_len[b] = r < 0 ? 0 : (uint32_t)r;

@@ -52,6 +52,10 @@ size_t  lz4o_max_output_size(size_t n);
 int64_t lz4o_compress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap);
 int64_t lz4o_compress_block_with_table(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                                        uint32_t *table4096, uint64_t stream_offset);
+int64_t lz4o_compress_block_dict(const uint8_t *in, size_t n, const uint8_t *dict, size_t dlen, uint8_t *out,
+                                 size_t cap);
+int     lz4o_decompress_block_dict(const uint8_t *in, size_t n, const uint8_t *dict, size_t dlen, uint8_t *out,
+                                   size_t cap, size_t *written, size_t *err_expected, size_t *err_actual);
 int64_t lz4o_compress_prepend_size(const uint8_t *in, size_t n, uint8_t *out, size_t cap);
 int     lz4o_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                               size_t *written, size_t *err_expected, size_t *err_actual);

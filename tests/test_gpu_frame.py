@@ -158,3 +158,53 @@ def test_config4_reduced_epochs(ctx):
     got = FrameInfo(block_size=BlockSize.Max4MB).header_bytes() + b"".join(parts) + b"\0\0\0\0"
     assert got == oracle.frame_compress(data, 7)
     assert frame.decompress_frame(got, ctx) == data.tobytes()
+
+
+# ---- BlockMode::Linked frames, decode side -----------------------------------------------------------
+
+def _linked_fixtures():
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_linked_frames import sources
+    src = sources()
+    d = os.path.join(os.path.dirname(__file__), "golden", "linked")
+    for m in json.load(open(os.path.join(d, "manifest.json"))):
+        f = open(os.path.join(d, m["file"]), "rb").read()
+        assert hashlib.sha256(f).hexdigest() == m["frame_sha256"]
+        yield m["file"], f, src[m["source"]]
+
+
+def test_linked_frames_decode_on_gpu(ctx):
+    """liblz4-written frames with linked blocks: the chain of blocks is resolved on the device
+    (lz4_decompress_blocks_linked), stored blocks included; content / block checksums verified."""
+    for name, f, want in _linked_fixtures():
+        assert frame.decompress_frame(f, ctx=ctx) == want, name
+    # a linked frame followed by an independent frame and another linked one
+    fx = list(_linked_fixtures())
+    indep = oracle.frame_compress(fx[0][2][:150000], 4)
+    cat = fx[3][1] + indep + fx[0][1]
+    assert frame.decompress_frame(cat, ctx=ctx) == fx[3][2] + fx[0][2][:150000] + fx[0][2]
+
+
+def test_linked_frame_errors_match_oracle(ctx):
+    import numpy as np
+    name, f, want = list(_linked_fixtures())[4]               # no checksums: corruption reaches the block decoder
+    rng = np.random.default_rng(5)
+    for t in range(40):
+        bad = bytearray(f)
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(16, len(bad)))] = int(rng.integers(0, 256))
+        cut = len(bad) if t % 4 else int(rng.integers(8, len(bad)))
+        blob = bytes(bad[:cut])
+        st, got, berr = oracle.frame_decompress(blob, len(want) + 70000)
+        out, err = frame.decompress_frame(blob, ctx=ctx, partial=True)
+        if st == 0:
+            assert err is None and out == got, t
+        else:
+            want_err = errors.error_from_status(st, berr, "")
+            assert type(err) is type(want_err), (t, st, berr, err)
+            if isinstance(err, errors.DecompressionError):
+                assert type(err.inner) is type(want_err.inner), (t, berr, err.inner)

@@ -269,7 +269,7 @@ def test_frame_vs_pyarrow():
     assert pa.decompress(f, decompressed_size=len(d), codec="lz4").to_pybytes() == d
     # pyarrow's own frames use linked blocks (LZ4F default), which is outside the GPU path's scope
     g = pa.compress(d, codec="lz4").to_pybytes()
-    assert oracle.frame_decompress(g, len(d))[0] in (0, oracle.FERR_LINKED_UNSUPPORTED)
+    assert oracle.frame_decompress(g, len(d))[:2] == (0, d)          # linked blocks are decoded too
 
 
 def test_frame_fresh_cont_epochs():
@@ -294,3 +294,94 @@ def test_frame_flush_shifts_phase():
     f = oracle.frame_compress(d, 4, 0, 100000)
     assert oracle.frame_decompress(f, len(d))[:2] == (0, d)
     assert f != oracle.frame_compress(d, 4)
+
+
+# ---- external dictionary ------------------------------------------------------------------------
+
+def _liblz4_dict():
+    if LIBLZ4 is None:
+        return None
+    LIBLZ4.LZ4_decompress_safe_usingDict.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_char_p, ctypes.c_int]
+    LIBLZ4.LZ4_decompress_safe_usingDict.restype = ctypes.c_int
+    return LIBLZ4
+
+
+def test_dict_reference_unit_tests():
+    from dict_cases import REF_INPUT
+    # compress.rs:892-911 test_dict
+    c = oracle.compress_with_dict(REF_INPUT, REF_INPUT)
+    assert len(c) < len(oracle.compress_block(REF_INPUT))
+    assert oracle.decompress_with_dict(c, len(REF_INPUT), REF_INPUT)[:2] == (0, REF_INPUT)
+    # compress.rs:913-919 test_dict_no_panic: a 3-byte dictionary is ignored
+    assert oracle.compress_with_dict(REF_INPUT, bytes([10, 12, 14])) == oracle.compress_block(REF_INPUT)
+    # decompress.rs:593-601: offset beyond dictionary + output
+    st = oracle.decompress_with_dict(bytes([0x0E, 255, 0, 0x70, 0, 0, 0, 0, 0, 0, 0]), 256, bytes(250))[0]
+    assert st == oracle.ERR_OFFSET_OOB
+    # compress.rs:921-950 test_dict_match_crossing, restated: decoding with the whole dictionary equals decoding
+    # with its first half as dictionary and its second half already in the output (virtual concatenation)
+    dct = b"0123456789ABCDE"
+    stream = bytes([0x0B, 5, 0, 0x50]) + b"vwxyz"
+    assert oracle.decompress_with_dict(stream, 64, dct)[:2] == (0, b"ABCDE" * 3 + b"vwxyz")
+
+
+def test_dict_roundtrip_and_foreign_decoder():
+    """Every dictionary case round-trips through the oracle and decodes identically with liblz4's
+    LZ4_decompress_safe_usingDict (the reference's interop strategy, tests/tests.rs:109-147)."""
+    from dict_cases import dict_cases
+    L = _liblz4_dict()
+    for name, data, dct in dict_cases():
+        c = oracle.compress_with_dict(data, dct)
+        st, o, _, _ = oracle.decompress_with_dict(c, len(data), dct)
+        assert (st, o) == (0, data), name
+        assert len(c) <= oracle.max_output_size(len(data)), name
+        if L is not None and len(data) > 0:
+            eff = dct[-65536:] if len(dct) > 3 else b""
+            buf = ctypes.create_string_buffer(len(data))
+            r = L.LZ4_decompress_safe_usingDict(c, buf, len(c), len(data), eff if eff else None, len(eff))
+            assert r == len(data) and buf.raw[: len(data)] == data, name
+
+
+def test_dict_helps_and_window_is_trimmed():
+    j = corpus.load("compression_66k_JSON.txt")
+    plain = oracle.compress_block(j[30000:50000])
+    with_dict = oracle.compress_with_dict(j[30000:50000], j[:30000])
+    assert len(with_dict) < len(plain)
+    # only the last 64 KiB of a dictionary are used (init_dict, compress.rs:571-575)
+    assert oracle.compress_with_dict(j[:5000], j) == oracle.compress_with_dict(j[:5000], j[-65536:])
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.binary(max_size=600), st.binary(max_size=600), st.integers(min_value=0, max_value=5))
+def test_dict_hypothesis_roundtrip(data, dct, k):
+    data = data * k
+    c = oracle.compress_with_dict(data, dct)
+    assert oracle.decompress_with_dict(c, len(data), dct)[:2] == (0, data)
+
+
+# ---- BlockMode::Linked frames, decode side (SURVEY.md §8 f-3) -----------------------------------------------------------
+
+def _linked_fixtures():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_linked_frames import sources
+    src = sources()
+    d = os.path.join(os.path.dirname(__file__), "golden", "linked")
+    for m in json.load(open(os.path.join(d, "manifest.json"))):
+        f = open(os.path.join(d, m["file"]), "rb").read()
+        assert sha(f) == m["frame_sha256"] and sha(src[m["source"]]) == m["source_sha256"]
+        yield m["file"], f, src[m["source"]]
+
+
+def test_linked_frames_from_liblz4_decode():
+    """Frames written by liblz4's LZ4F with linked blocks (incl. stored blocks, checksums, an LZ4HC parse) decode to
+    their sources; a block may reach up to 64 KiB into the frame's earlier output (frame/decompress.rs:196-305)."""
+    for name, f, want in _linked_fixtures():
+        st, got, berr = oracle.frame_decompress(f, len(want) + 64)
+        assert (st, got) == (0, want), name
+
+
+def test_linked_frame_corruption_is_detected():
+    name, f, want = next(_linked_fixtures())                   # has block + content checksums
+    bad = bytearray(f); bad[len(f) // 2] ^= 0x55
+    assert oracle.frame_decompress(bytes(bad), len(want) + 64)[0] == oracle.FERR_BLOCK_CHECKSUM
