@@ -98,6 +98,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(prefix: str):
+    """(kernel name, DRAM bytes per launch) of the first kernel whose name contains `prefix` in the committed
+    ncu --set full summary of this workload (profiles/r1_ncu_summary.json), or (prefix, None)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_summary.json")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        for e in json.load(open(path)):
+            if prefix in e.get("kernel", ""):
+                tot = 0.0
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v, u = e[k].split()
+                    tot += float(v) * unit[u]
+                name = e["kernel"].replace("void ", "").split("(")[0].replace("unsigned short", "u16").replace("(int)", "")
+                return name, tot
+    except Exception:                                           # noqa: BLE001
+        pass
+    return prefix, None
+
+
 def build_workload(nblocks: int, rank: int):
     from lz4_flex_b200 import corpus
     total = nblocks * BLOCK
@@ -349,6 +368,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    k1_name, k1_traffic = ncu_traffic("lz4_compress_blocks")
+    k2_name, k2_traffic = ncu_traffic("lz4_decompress_blocks")
     mib_rank = nb * BLOCK / 2**20
     ms_per_step = elapsed_ms / args.steps
     value = world * mib_rank / (ms_per_step / 1e3)
@@ -374,15 +395,15 @@ def run_ours(args):
                    "ratio": comp_bytes / (nb * BLOCK)},
         "compress_mibs": world * mib_rank / (t_c / 1e3), "decompress_mibs": world * mib_rank / (t_d / 1e3),
         "compress_ms": t_c, "decompress_ms": t_d,
-        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-        # (profiles/r1_ncu_summary.json): compress 1.713 + 0.249 GB, decompress 2.238 + 1.059 GB
-        "roofline": {"kernel": "lz4_compress_blocks<u16,4>", "bound": "hbm", "achieved": ach_c, "peak": peak,
-                     "unit": "GB/s", "frac": ach_c / peak, "traffic": 1.962e9 if nb == NBLOCKS_DEFAULT else None,
+        # traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture of
+        # the same workload (profiles/r1_ncu_summary.json; see ncu_traffic())
+        "roofline": {"kernel": k1_name, "bound": "hbm", "achieved": ach_c, "peak": peak,
+                     "unit": "GB/s", "frac": ach_c / peak, "traffic": k1_traffic if nb == NBLOCKS_DEFAULT else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes},
-        "roofline_decompress": {"kernel": "lz4_decompress_blocks<8,0>", "bound": "hbm", "achieved": ach_d, "peak": peak,
+        "roofline_decompress": {"kernel": k2_name, "bound": "hbm", "achieved": ach_d, "peak": peak,
                                 "unit": "GB/s", "frac": ach_d / peak,
-                                "traffic": 3.297e9 if nb == NBLOCKS_DEFAULT else None, "peak_source": peak_src,
+                                "traffic": k2_traffic if nb == NBLOCKS_DEFAULT else None, "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": alg_bytes},
         "cpu_baseline": {"value": cpu_all["roundtrip_mibs"], "unit": "MiB/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_blocks} of the {nb} blocks, compress+decompress, best of 3, "

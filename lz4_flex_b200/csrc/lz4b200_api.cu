@@ -254,6 +254,10 @@ struct lz4b200_ctx {
     int enc_smem_kb = 0;                      // LZ4B200_ENC_SMEM_KB: shared-memory carve-out used by the encoder
     int enc16s_ctas_per_sm = 0, enc32s_ctas_per_sm = 0;   // split (matcher+emitter) encoder
     int high_priority = 0;                    // lz4b200_ctx_set_priority(ctx, 1): pipeline streams get the highest priority
+    int enc_gtab = 71;                        // global-table encoder: 10*matchers + emitters per CTA (62|71); LZ4B200_ENC_GTAB=0: off
+    int enc_gtab_smem = 0;
+    DevBuf<uint16_t> d_gtab16;
+    const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
     int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
     int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
@@ -354,6 +358,31 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         }
         uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * per_sm);
 #if ENC_SPLIT
+        // Global-table encoder when the batch has more blocks than the shared-memory-table kernel keeps in flight
+        // (24 per SM): 56 slower chains per SM then beat 24 faster ones (17.3 vs 20.1 ms per GiB of 64 KiB blocks);
+        // with fewer blocks the shorter chain of the shared-memory tables wins.
+        if (ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+            // global-table encoder: 8 warps per CTA, 8 CTAs per SM
+            const int m = ctx->enc_gtab / 10, e = ctx->enc_gtab % 10;
+            want = (a.nblocks + m - 1) / m;
+            grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 8u);
+            // one table region per concurrently running launch (the host pipeline launches from up to 8 lanes):
+            // the ticket block doubles as the region selector
+            const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;             // u16 entries
+            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
+            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
+            uint16_t *gt = ctx->d_gtab16.p + slot * region;
+            // LZ4B200_ENC_GTAB = 10*matchers + emitters per CTA; LZ4B200_ENC_GTAB_SMEM = how many of the matchers keep
+            // their table in shared memory (0, 2 or 3)
+            const int ks = ctx->enc_gtab_smem;
+            if (m == 6 && e == 2) lz4_compress_blocks_gtab<uint16_t, 6, 2, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            else if (m == 4 && e == 4) lz4_compress_blocks_gtab<uint16_t, 4, 4, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            else if (ks == 2) lz4_compress_blocks_gtab<uint16_t, 7, 1, 2><<<grid, 256, 2 * 8192, s>>>(a, tickets + 2, gt);
+            else if (ks == 3) {
+                grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 7u);
+                lz4_compress_blocks_gtab<uint16_t, 7, 1, 3><<<grid, 256, 3 * 8192, s>>>(a, tickets + 2, gt);
+            } else lz4_compress_blocks_gtab<uint16_t, 7, 1, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+        } else
         if (!ctx->enc_single_warp || a.dict_len) {
             want = (a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs;
             grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
@@ -483,6 +512,8 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         if (v == 8 || v == 16 || v == 32) ctx->enc_group_override = v;
     }
     if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAB_SMEM")) ctx->enc_gtab_smem = atoi(g);
     if (getenv("LZ4B200_DEBUG"))
         fprintf(stderr, "lz4b200: SMs %d, CTAs/SM: dec %d, enc16 %d, enc32 %d, enc16-split %d (x%d pairs), enc32-split %d (x%d pairs)\n",
                 ctx->sm_count, ctx->dec_ctas_per_sm, ctx->enc16_ctas_per_sm, ctx->enc32_ctas_per_sm,
@@ -635,10 +666,10 @@ namespace {
 constexpr int kMaxLanes = 8;
 // Lanes in flight.  A compress chunk occupies its lane for H2D + kernel (one block's serial chain, ~5 ms) + the
 // size read-back + D2H, ~10 ms in all, so three lanes cap the call at ~3.5 ms per 128 MiB chunk whatever the
-// kernel does (measured 30 ms per GiB); six lanes leave the kernel / PCIe as the bound.  LZ4B200_LANES overrides.
+// kernel does (measured 30 ms per GiB); eight lanes leave the kernel / PCIe as the bound (26.8 ms).  LZ4B200_LANES overrides.
 static int lanes_in_use()
 {
-    static const int v = [] { const char *e = getenv("LZ4B200_LANES"); int k = e ? atoi(e) : 6; return k < 1 ? 1 : (k > kMaxLanes ? kMaxLanes : k); }();
+    static const int v = [] { const char *e = getenv("LZ4B200_LANES"); int k = e ? atoi(e) : 8; return k < 1 ? 1 : (k > kMaxLanes ? kMaxLanes : k); }();
     return v;
 }
 // decompress: a chunk's kernel lasts at least one block's serial chain (~1 ms for 64 KiB of JSON) however few blocks
@@ -685,6 +716,7 @@ lz4b200_status pipeline_init(lz4b200_ctx *ctx, Pipeline &p)
     CTX_CUDA(ctx, cudaEventCreateWithFlags(&p.desc_ready, cudaEventDisableTiming));
     CTX_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&p.d_tickets), kMaxLanes * 8 * sizeof(uint32_t)));
     CTX_CUDA(ctx, cudaMemset(p.d_tickets, 0, kMaxLanes * 8 * sizeof(uint32_t)));
+    ctx->pipe_tickets = p.d_tickets;
     p.ready = true;
     return LZ4B200_OK;
 }

@@ -18,6 +18,9 @@
 // Hand-off: two halves of 16 tuples, mbarriers "full[h]" / "empty[h]" per pair in shared memory — the matcher
 // never waits unless the emitter is two batches behind.
 #pragma once
+#ifndef ENC_FIRST_WIDTH
+#define ENC_FIRST_WIDTH 32  // lanes probing in the first round of a sequence (8: 22.4 vs 20.6 ms — the extra round costs more than the traffic it saves)
+#endif
 #ifndef ENC_FASTW
 #define ENC_FASTW 1     // 1: settle slot collisions of the first <= 4 probes with shuffles instead of match.any
 #endif
@@ -194,7 +197,59 @@ struct InputWindow {
 // ---------------------------------------------------------------------------------------------
 // matcher: the search half of compress_internal.  Table semantics identical to encode_block_v1.
 // ---------------------------------------------------------------------------------------------
-template <typename TabT>
+// Table accessors.  kGT = false: the table lives in shared memory (plain indexing, LDS/STS).  kGT = true: it lives
+// in global memory and is read/written through L2 (ld/st.global.cg): ~250 cycles instead of 29 per access, but no
+// shared memory per matcher, so the matchers per SM are bounded by warps and registers instead of by 8 KiB tables.
+// Global tables are accessed with an L2 evict_last policy (createpolicy is a constant: it folds into the access
+// descriptor): 66 MB of tables must stay resident in the 126 MB L2 while ~0.5 GB of input streams through it —
+// without the hint the tables are evicted and every probe becomes a DRAM read (27.6 GB read per GiB compressed).
+__device__ __forceinline__ uint64_t l2_keep_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <bool kGT>
+__device__ __forceinline__ uint32_t tab_get(const uint16_t *tab, uint32_t slot)
+{
+    if constexpr (kGT) {
+        uint16_t v;
+        asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
+        return v;
+    } else return tab[slot];
+}
+template <bool kGT>
+__device__ __forceinline__ uint32_t tab_get(const uint32_t *tab, uint32_t slot)
+{
+    if constexpr (kGT) {
+        uint32_t v;
+        asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
+        return v;
+    } else return tab[slot];
+}
+template <bool kGT>
+__device__ __forceinline__ void tab_put(uint16_t *tab, uint32_t slot, uint32_t v)
+{
+    if constexpr (kGT)
+        asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(tab + slot), "h"((uint16_t)v), "l"(l2_keep_policy()) : "memory");
+    else tab[slot] = (uint16_t)v;
+}
+template <bool kGT>
+__device__ __forceinline__ void tab_put(uint32_t *tab, uint32_t slot, uint32_t v)
+{
+    if constexpr (kGT)
+        asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(tab + slot), "r"(v), "l"(l2_keep_policy()) : "memory");
+    else tab[slot] = v;
+}
+template <bool kGT>
+__device__ __forceinline__ void tab_fill16(uint4 *at, uint32_t f)
+{
+    if constexpr (kGT)
+        asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(at), "r"(f), "l"(l2_keep_policy()) : "memory");
+    else *at = make_uint4(f, f, f, f);
+}
+
+template <typename TabT, bool kGT = false>
 __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, uint32_t *ring,
                                             bool cont, bool h5, SeqProducer &pr, uint32_t lane)
 {
@@ -209,7 +264,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         const uint32_t f = cont ? 0xffffffffu : 0u;
         uint4 *t128 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll 4
-        for (uint32_t i = lane; i < words; i += 32) t128[i] = make_uint4(f, f, f, f);
+        for (uint32_t i = lane; i < words; i += 32) tab_fill16<kGT>(t128 + i, f);
         __syncwarp();
     }
     const WordView view(src);
@@ -222,7 +277,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
     if (!cont) {                                                // compress.rs:353-359
         uint32_t lo, hi; view.ro5(0, lo, hi);
         const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) tab[s] = 0;
+        if (lane == 0) tab_put<kGT>(tab, s, 0u);
         cur = 1;
         __syncwarp();
     }
@@ -231,14 +286,18 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
 #if ENC_WINDOW
         win.advance(cur + win.mis, lane);
 #endif
-        uint32_t base = cur, stride = 1, cand, mpos;
+        // ENC_FIRST_WIDTH < 32 (A/B aid): the first 32 probes (step 1) go in two rounds of ENC_FIRST_WIDTH and
+        // 32 - ENC_FIRST_WIDTH lanes, trading speculative table/candidate traffic for an extra round on long searches.
+        uint32_t base = cur, stride = 1, width = ENC_FIRST_WIDTH, cand, mpos;
         bool in_win = ENC_WINDOW != 0;                          // first batch: probe bytes come from the ring
         for (;;) {                                              // probe batches: compress.rs:373-439
             const uint32_t p = base + lane * stride;
-            const bool term = p > last_probe;
+            const bool act = lane < width;
+            const bool term = act && p > last_probe;
+            const bool live = act && !term;
             uint32_t v4, hi;
             if (in_win) win.ro5(p + win.mis, v4, hi);           // term lanes read ring bytes they never use
-            else view.ro5(term ? 0u : p, v4, hi);
+            else view.ro5(live ? p : 0u, v4, hi);
             uint32_t s2 = 0xffffffffu;
             if (ri) {
                 // The re-insert of the previous sequence (compress.rs:460-461) rides along with the first probe loads.
@@ -246,7 +305,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
                 if (ENC_WINDOW) win.ro5(cur - 2u + win.mis, lo2, hi2); else view.ro5(cur - 2u, lo2, hi2);
                 s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
 #if !ENC_RI_PATCH
-                if (lane == 0) tab[s2] = (TabT)(cur - 2u);
+                if (lane == 0) tab_put<kGT>(tab, s2, cur - 2u);
                 __syncwarp();
                 s2 = 0xffffffffu;
 #endif
@@ -254,7 +313,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             }
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
             uint32_t cnd = kInvalid;
-            if (!term) cnd = tab[key]; else key = 0x10000u | lane;
+            if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
 #if ENC_RI_PATCH
             // Nothing waits for the re-insert's table write: a probe on the same slot takes cur-2 directly and the
             // write itself is made with this batch's commits (dropped if a committed probe overwrites the slot).
@@ -266,7 +325,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             // speculation was exact.  For w0 <= 3 (89 % of JSON sequences) that is settled with three shuffles;
             // match.any — whose latency grows with the number of distinct keys, ~900 cycles for 32 — only runs
             // for the rest.
-            bool chk = !term && cnd != kInvalid && p - cnd <= 65535u;
+            bool chk = live && cnd != kInvalid && p - cnd <= 65535u;
             bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
             uint32_t hits = __ballot_sync(kFull, hit);
             const uint32_t terms = __ballot_sync(kFull, term);
@@ -300,14 +359,14 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
                 return;
             }
             // commit the table writes of probes 0..win (last writer per slot wins)
-            const uint32_t upto = win < 32u ? win : 31u;
+            const uint32_t upto = win < 32u ? win : width - 1u;
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
-            if (lane <= upto && (31u - __clz(mine)) == lane) tab[key] = (TabT)p;
+            if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, p);
 #if ENC_RI_PATCH
             if (s2 != 0xffffffffu) {                            // uniform: first batch after a match
                 const uint32_t dups = __ballot_sync(kFull, key == s2 && lane <= upto);
-                if (lane == 0 && dups == 0u) tab[s2] = (TabT)(cur - 2u);
+                if (lane == 0 && dups == 0u) tab_put<kGT>(tab, s2, cur - 2u);
             }
 #endif
             __syncwarp();
@@ -316,8 +375,13 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
                 cand = __shfl_sync(kFull, cnd, win);
                 break;
             }
-            base += 32u * stride;
-            stride++;
+            base += width * stride;
+            if (ENC_FIRST_WIDTH < 32 && base == cur + ENC_FIRST_WIDTH) {
+                width = 32u - ENC_FIRST_WIDTH;                  // the rest of the step-1 probes
+            } else {
+                width = 32u;
+                stride++;
+            }
             in_win = false;
         }
         const uint32_t dist = mpos - cand;
@@ -499,6 +563,68 @@ __device__ __forceinline__ uint8_t *put_len_ext(uint8_t *p, uint32_t v)     // v
     return p;
 }
 
+// Emits one batch of tuples (one per lane) at output cursor `o`; returns the bytes produced.
+__device__ __forceinline__ uint32_t emit_batch(const uint8_t *__restrict__ src, uint8_t *dst, uint32_t o, const uint4 e,
+                                               uint32_t cnt, uint32_t lane)
+{
+    const bool valid = lane < cnt;
+    const bool tail = e.z == 0;                            // last literals: no match part
+    const uint32_t lit = valid ? (tail ? e.w : e.y) - e.x : 0u;
+    const uint32_t extra = (valid && !tail) ? e.w - e.y - 4u : 0u;
+    const uint32_t lit_ext = lit >= 15u ? (lit - 15u) / 255u + 1u : 0u;
+    const uint32_t m_ext = extra >= 15u ? (extra - 15u) / 255u + 1u : 0u;
+    const uint32_t size = valid ? 1u + lit_ext + lit + (tail ? 0u : 2u + m_ext) : 0u;
+    uint32_t incl = size;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    uint8_t *p = dst + o + (incl - size);
+    uint8_t *lit_at = p;
+    if (valid) {
+        *p++ = (uint8_t)(((lit < 15u ? lit : 15u) << 4) | (tail ? 0u : (extra < 15u ? extra : 15u)));
+        if (lit >= 15u) p = put_len_ext(p, lit - 15u);
+        lit_at = p;
+        if (lit <= kSmallLit) {
+            // 8 bytes per round trip (loads first, then stores): a byte-at-a-time loop pays one L2 latency per byte
+            const uint8_t *s = src + e.x;
+            for (uint32_t i = 0; i < lit; i += 8u) {
+                uint8_t c[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8u; k++) c[k] = (i + k < lit) ? __ldg(s + i + k) : (uint8_t)0;
+#pragma unroll
+                for (uint32_t k = 0; k < 8u; k++) if (i + k < lit) p[i + k] = c[k];
+            }
+        }
+        p += lit;
+        if (!tail) {
+            p[0] = (uint8_t)e.z; p[1] = (uint8_t)(e.z >> 8);
+            p += 2;
+            if (extra >= 15u) put_len_ext(p, extra - 15u);
+        }
+    }
+    // long literal runs: the whole warp copies them, one run at a time
+    uint32_t big = __ballot_sync(kFull, valid && lit > kSmallLit);
+    while (big) {
+        const uint32_t l = (uint32_t)__ffs(big) - 1u;
+        big &= big - 1u;
+        const uint32_t from = __shfl_sync(kFull, e.x, l), len = __shfl_sync(kFull, lit, l);
+        const uint32_t at = __shfl_sync(kFull, (uint32_t)(lit_at - dst), l);
+        const uint8_t *s = src + from;
+        uint8_t *d = dst + at;
+        uint32_t i = lane;
+        for (; i + 96u < len; i += 128u) {
+            const uint8_t c0 = __ldg(s + i), c1 = __ldg(s + i + 32), c2 = __ldg(s + i + 64), c3 = __ldg(s + i + 96);
+            d[i] = c0; d[i + 32] = c1; d[i + 64] = c2; d[i + 96] = c3;
+        }
+        for (; i < len; i += 32u) d[i] = __ldg(s + i);
+    }
+    return total;
+}
+
+// Emitter serving one matcher (lz4_compress_blocks_split).
 __device__ __forceinline__ void emit_loop(const BatchArgs &a, const uint4 *q, const volatile uint32_t *meta, uint64_t *bars,
                                           uint32_t lane)
 {
@@ -515,56 +641,53 @@ __device__ __forceinline__ void emit_loop(const BatchArgs &a, const uint4 *q, co
         if (lane == 0) mbar_arrive(bars + 2 + h);              // tuples are in registers: the half may be refilled
         if (b == kExitBlock) break;
         if (fl & 1u) { src = a.in + a.in_off[b]; dst = a.out + a.out_off[b]; o = 0; }
-
-        const bool valid = lane < cnt;
-        const bool tail = e.z == 0;                            // last literals: no match part
-        const uint32_t lit = valid ? (tail ? e.w : e.y) - e.x : 0u;
-        const uint32_t extra = (valid && !tail) ? e.w - e.y - 4u : 0u;
-        const uint32_t lit_ext = lit >= 15u ? (lit - 15u) / 255u + 1u : 0u;
-        const uint32_t m_ext = extra >= 15u ? (extra - 15u) / 255u + 1u : 0u;
-        const uint32_t size = valid ? 1u + lit_ext + lit + (tail ? 0u : 2u + m_ext) : 0u;
-        uint32_t incl = size;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, incl, d);
-            if (lane >= (uint32_t)d) incl += t;
-        }
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
-        uint8_t *p = dst + o + (incl - size);
-        uint8_t *lit_at = p;
-        if (valid) {
-            *p++ = (uint8_t)(((lit < 15u ? lit : 15u) << 4) | (tail ? 0u : (extra < 15u ? extra : 15u)));
-            if (lit >= 15u) p = put_len_ext(p, lit - 15u);
-            lit_at = p;
-            if (lit <= kSmallLit) {
-                const uint8_t *s = src + e.x;
-                for (uint32_t i = 0; i < lit; i++) p[i] = __ldg(s + i);
-            }
-            p += lit;
-            if (!tail) {
-                p[0] = (uint8_t)e.z; p[1] = (uint8_t)(e.z >> 8);
-                p += 2;
-                if (extra >= 15u) put_len_ext(p, extra - 15u);
-            }
-        }
-        // long literal runs: the whole warp copies them, one run at a time
-        uint32_t big = __ballot_sync(kFull, valid && lit > kSmallLit);
-        while (big) {
-            const uint32_t l = (uint32_t)__ffs(big) - 1u;
-            big &= big - 1u;
-            const uint32_t from = __shfl_sync(kFull, e.x, l), len = __shfl_sync(kFull, lit, l);
-            const uint32_t at = __shfl_sync(kFull, (uint32_t)(lit_at - dst), l);
-            const uint8_t *s = src + from;
-            uint8_t *d = dst + at;
-            uint32_t i = lane;
-            for (; i + 96u < len; i += 128u) {
-                const uint8_t c0 = __ldg(s + i), c1 = __ldg(s + i + 32), c2 = __ldg(s + i + 64), c3 = __ldg(s + i + 96);
-                d[i] = c0; d[i + 32] = c1; d[i + 64] = c2; d[i + 96] = c3;
-            }
-            for (; i < len; i += 32u) d[i] = __ldg(s + i);
-        }
-        o += total;
+        o += emit_batch(src, dst, o, e, cnt, lane);
         if ((fl & 2u) && lane == 0) { a.out_len[b] = o; a.status[b] = LZ4B200_OK; }
+    }
+}
+
+// Emitter serving kR matchers (lz4_compress_blocks_gtab): polls their rings in turn; per-ring state in shared memory.
+struct EmitState { const uint8_t *src; uint8_t *dst; uint32_t o, j; };
+
+template <int kR>
+__device__ __forceinline__ void emit_loop_multi(const BatchArgs &a, const uint4 *q0, const volatile uint32_t *meta0,
+                                                uint64_t *bars0, EmitState *st, uint32_t lane)
+{
+    if (lane < (uint32_t)kR) { st[lane].src = nullptr; st[lane].dst = nullptr; st[lane].o = 0; st[lane].j = 0; }
+    __syncwarp();
+    uint32_t live = (1u << kR) - 1u;
+    while (live) {
+        bool progress = false;
+#pragma unroll 1
+        for (int i = 0; i < kR; i++) {
+            if (!((live >> i) & 1u)) continue;
+            const uint4 *q = q0 + i * 2 * kSeqBatchEntries;
+            const volatile uint32_t *meta = meta0 + i * 8;
+            uint64_t *bars = bars0 + i * 4;
+            const uint32_t j = st[i].j, h = j & 1u;
+            uint32_t ready;
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ready) : "r"(smem_addr(bars + h)), "r"((j >> 1) & 1u) : "memory");
+            if (!ready) continue;
+            progress = true;
+            const uint32_t b = meta[h * 4 + 0], cnt = meta[h * 4 + 1], fl = meta[h * 4 + 2];
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lane < cnt && b != kExitBlock) e = q[h * kSeqBatchEntries + lane];
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bars + 2 + h); st[i].j = j + 1u; }
+            if (b == kExitBlock) { live &= ~(1u << i); __syncwarp(); continue; }
+            if ((fl & 1u) && lane == 0) { st[i].src = a.in + a.in_off[b]; st[i].dst = a.out + a.out_off[b]; st[i].o = 0; }
+            __syncwarp();
+            const uint32_t o = st[i].o;
+            const uint32_t total = emit_batch(st[i].src, st[i].dst, o, e, cnt, lane);
+            __syncwarp();
+            if (lane == 0) {
+                st[i].o = o + total;
+                if (fl & 2u) { a.out_len[b] = o + total; a.status[b] = LZ4B200_OK; }
+            }
+            __syncwarp();
+        }
+        if (!progress) __nanosleep(ENC_EMIT_SLEEP_NS ? ENC_EMIT_SLEEP_NS : 200);
     }
 }
 
@@ -618,6 +741,61 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0, lane);
     retire_warp(tickets, gridDim.x * kPairs);
+}
+
+// The per-warp block loop of a matcher (shared by the kernels below).
+template <typename TabT, bool kGT>
+__device__ __forceinline__ void matcher_loop(const BatchArgs &a, uint32_t *tickets, TabT *tab, SeqProducer &pr, uint32_t lane)
+{
+    constexpr bool kSmall = sizeof(TabT) == 2;
+    for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
+        const uint32_t n = a.in_len[b];
+        if ((n <= 65536u) != kSmall) continue;
+        const uint32_t fl = a.flags ? a.flags[b] : 0u;
+        if ((uint64_t)a.out_cap[b] < max_output_size_dev(n)) {              // compress.rs:338-340
+            if (lane == 0) { a.out_len[b] = 0; a.status[b] = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; }
+            continue;
+        }
+        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
+        pr.block = b; pr.first = 1;
+        match_block<TabT, kGT>(a.in + a.in_off[b], n, tab, nullptr, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
+    }
+    pr.block = kExitBlock; pr.first = 0;
+    pr.flush(0, lane);
+}
+
+// Many-matcher variant: kM matcher warps + kE emitter warps per CTA (kM a multiple of kE).  The first kS matchers
+// of a CTA keep their table in shared memory; the others keep it in global memory (gtab, 4096 entries per matcher
+// of the grid, held in L2 by an evict_last policy).  Shared-memory tables cap an SM at 24 matchers; global tables
+// cost ~250 cycles per access but none of the 228 KB, so with 32 registers per thread all 64 warps of an SM work:
+// e.g. 8 CTAs x (2 shared + 5 global matchers + 1 emitter).  Blocks are pulled from one ticket queue, so the faster
+// shared-memory matchers simply take more of them.
+template <typename TabT, int kM, int kE, int kS>
+__global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
+lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
+{
+    constexpr int kR = kM / kE;
+    static_assert(kM % kE == 0, "every emitter serves the same number of matchers");
+    extern __shared__ __align__(16) uint8_t smem_raw[];      // kS tables
+    __shared__ __align__(16) uint4 q_s[kM * 2 * kSeqBatchEntries];
+    __shared__ uint32_t meta_s[kM * 8];
+    __shared__ __align__(8) uint64_t bars_s[kM * 4];
+    __shared__ EmitState st_s[kM];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x < (uint32_t)kM * 4u) mbar_init(bars_s + threadIdx.x, 1u);
+    __syncthreads();
+    if (warp >= (uint32_t)kM) {
+        const uint32_t e = warp - kM;
+        emit_loop_multi<kR>(a, q_s + e * kR * 2 * kSeqBatchEntries, meta_s + e * kR * 8, bars_s + e * kR * 4,
+                            st_s + e * kR, lane);
+        return;
+    }
+    SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    if (warp < (uint32_t)kS)
+        matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
+    else
+        matcher_loop<TabT, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
+    retire_warp(tickets, gridDim.x * kM);
 }
 
 template <typename TabT, int kPairs>

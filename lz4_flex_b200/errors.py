@@ -115,7 +115,7 @@ class IoError(FrameError):
 
 
 class LinkedBlocksUnsupported(FrameError):
-    """BlockMode::Linked has a serial dependence between blocks and is not on the GPU path."""
+    """BlockMode::Linked is not offered by the ENCODER (one serial chain per frame); the decoder handles it."""
 
 
 class CudaError(RuntimeError):

@@ -1,4 +1,4 @@
-"""lz4_flex::frame, B200 edition (independent-block mode).
+"""lz4_flex::frame, B200 edition (encoder: independent-block mode; decoder: independent and linked blocks).
 
 FrameInfo / BlockSize / BlockMode / FrameEncoder / FrameDecoder with the reference's names and behaviour
 (src/frame/header.rs:39-192, src/frame/compress.rs:62-438, src/frame/decompress.rs:48-422).  The container
@@ -7,8 +7,10 @@ and decompressed in GPU batches through the C ABI.  Block boundaries, the stored
 each block's parse mode (FRESH for the first block of a table epoch, CONT afterwards) follow
 FrameEncoder::write/write_block exactly, so the produced frame is byte-identical to lz4_flex's.
 
-BlockMode::Linked creates a serial dependence between blocks and is not on the GPU path
-(LinkedBlocksUnsupported).
+BlockMode::Linked chains every block to its frame's earlier output.  The DECODER handles it on the device
+(lz4_decompress_blocks_linked: a block waits for the predecessors an offset reaches into), so frames written by
+`lz4` / LZ4F / pyarrow with their default linked blocks decode; the ENCODER refuses it (LinkedBlocksUnsupported):
+a linked encode is one serial chain per frame, which is not what a GPU batch path is for.
 """
 from __future__ import annotations
 
