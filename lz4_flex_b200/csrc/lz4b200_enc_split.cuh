@@ -18,6 +18,9 @@
 // Hand-off: two halves of 16 tuples, mbarriers "full[h]" / "empty[h]" per pair in shared memory — the matcher
 // never waits unless the emitter is two batches behind.
 #pragma once
+#ifndef ENC_GTAB_L1
+#define ENC_GTAB_L1 0   // 1: global-table reads may hit L1 (same-SM coherent); 0: L2 only
+#endif
 #ifndef ENC_FIRST_WIDTH
 #define ENC_FIRST_WIDTH 32  // lanes probing in the first round of a sequence (8: 22.4 vs 20.6 ms — the extra round costs more than the traffic it saves)
 #endif
@@ -214,7 +217,11 @@ __device__ __forceinline__ uint32_t tab_get(const uint16_t *tab, uint32_t slot)
 {
     if constexpr (kGT) {
         uint16_t v;
+#if ENC_GTAB_L1
+        asm volatile("ld.global.ca.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
+#else
         asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
+#endif
         return v;
     } else return tab[slot];
 }
