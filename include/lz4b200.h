@@ -60,7 +60,7 @@ typedef enum lz4b200_status {
     LZ4B200_FRAME_SKIPPABLE = 111,           /* Error::SkippableFrame                   */
     LZ4B200_FRAME_DICTIONARY = 112,          /* Error::DictionaryNotSupported           */
     LZ4B200_FRAME_IO_EOF = 113,              /* Error::IoError(UnexpectedEof)           */
-    LZ4B200_FRAME_LINKED_UNSUPPORTED = 114,  /* BlockMode::Linked: not on the GPU path  */
+    LZ4B200_FRAME_LINKED_UNSUPPORTED = 114,  /* BlockMode::Linked asked of the ENCODER (the decoder handles it) */
     LZ4B200_FRAME_OUTPUT_FULL = 115,         /* caller's flat output buffer exhausted   */
 
     LZ4B200_INVALID_ARGUMENT = 200,
@@ -230,7 +230,7 @@ lz4b200_status lz4b200_decompress_batch_host_with_dict(lz4b200_ctx *ctx,
     uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
     uint32_t *out_len, int32_t *status, uint64_t *err_expected, size_t nblocks);
 
-/* ---- frame format (independent blocks) -----------------------------------------------------
+/* ---- frame format (encoder: independent blocks; decoder: independent and linked) -------------
  * FrameInfo — src/frame/header.rs:130-192. */
 typedef struct lz4b200_frame_info {
     int32_t block_size_id;     /* BlockSize: 0 Auto, 4 64KB, 5 256KB, 6 1MB, 7 4MB (header.rs:39-53) */
@@ -238,7 +238,7 @@ typedef struct lz4b200_frame_info {
     int32_t content_checksum;  /* FrameInfo::content_checksum  */
     int32_t has_content_size;  /* FrameInfo::content_size.is_some() */
     uint64_t content_size;     /* FrameInfo::content_size      */
-    int32_t linked;            /* BlockMode::Linked — rejected (LZ4B200_FRAME_LINKED_UNSUPPORTED) */
+    int32_t linked;            /* BlockMode::Linked — the encoder rejects it (LZ4B200_FRAME_LINKED_UNSUPPORTED) */
     int32_t reserved;
 } lz4b200_frame_info;
 
@@ -274,7 +274,9 @@ size_t lz4b200_frame_write_header(const lz4b200_frame_info *info, uint8_t *out, 
 
 /* FrameDecoder::new(r).read_to_end() over all concatenated frames
  *   — src/frame/decompress.rs:109-342.  Host pointers.  *block_status receives the block
- * decoder's code when the result is FRAME_DECOMPRESSION_ERROR. */
+ * decoder's code when the result is FRAME_DECOMPRESSION_ERROR.  Frames with linked blocks
+ * (frame/decompress.rs:196-222, 277-305; what `lz4`, LZ4F and pyarrow write by default) are decoded
+ * too: their blocks form a dependency chain that the device resolves in stream order. */
 lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
                                         uint8_t *out, size_t cap, size_t *written,
                                         int *block_status);

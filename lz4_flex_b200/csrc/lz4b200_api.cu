@@ -256,11 +256,14 @@ struct lz4b200_ctx {
     int high_priority = 0;                    // lz4b200_ctx_set_priority(ctx, 1): pipeline streams get the highest priority
     int enc_gtab = 71;                        // global-table encoder: 10*matchers + emitters per CTA (62|71); LZ4B200_ENC_GTAB=0: off
     int enc_gtab_smem = 0;
+    int enc_gtab_carveout = -1;               // LZ4B200_ENC_GTAB_CARVEOUT=<percent of shared memory>
+    bool enc_gtab_carveout_set = false;
     DevBuf<uint16_t> d_gtab16;
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
     int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
     int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
+    int dec_conv = 0;                         // LZ4B200_DEC_CONV=1: warp-converged decoder loop (A/B aid)
     int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
     int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32 (tuning aid)
     std::string last_error;
@@ -311,6 +314,7 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
     uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
     uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * (ctx->dec_ctas_override ? ctx->dec_ctas_override : 16)));
     if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    else if (ctx->dec_conv) lz4_decompress_blocks_conv<G><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     else if (ctx->dec_batched) lz4_decompress_blocks<G, 1, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     else lz4_decompress_blocks<G, 0, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     CTX_CUDA(ctx, cudaGetLastError());
@@ -375,6 +379,11 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             // LZ4B200_ENC_GTAB = 10*matchers + emitters per CTA; LZ4B200_ENC_GTAB_SMEM = how many of the matchers keep
             // their table in shared memory (0, 2 or 3)
             const int ks = ctx->enc_gtab_smem;
+            if (ctx->enc_gtab_carveout >= 0 && !ctx->enc_gtab_carveout_set) {      // tuning aid: L1 vs shared memory split
+                cudaFuncSetAttribute(lz4_compress_blocks_gtab<uint16_t, 7, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     ctx->enc_gtab_carveout);
+                ctx->enc_gtab_carveout_set = true;
+            }
             if (m == 6 && e == 2) lz4_compress_blocks_gtab<uint16_t, 6, 2, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else if (m == 4 && e == 4) lz4_compress_blocks_gtab<uint16_t, 4, 4, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else if (ks == 2) lz4_compress_blocks_gtab<uint16_t, 7, 1, 2><<<grid, 256, 2 * 8192, s>>>(a, tickets + 2, gt);
@@ -514,12 +523,14 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAB_SMEM")) ctx->enc_gtab_smem = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAB_CARVEOUT")) ctx->enc_gtab_carveout = atoi(g);
     if (getenv("LZ4B200_DEBUG"))
         fprintf(stderr, "lz4b200: SMs %d, CTAs/SM: dec %d, enc16 %d, enc32 %d, enc16-split %d (x%d pairs), enc32-split %d (x%d pairs)\n",
                 ctx->sm_count, ctx->dec_ctas_per_sm, ctx->enc16_ctas_per_sm, ctx->enc32_ctas_per_sm,
                 ctx->enc16s_ctas_per_sm, kEnc16Pairs, ctx->enc32s_ctas_per_sm, kEnc32Pairs);
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
+    if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) ctx->dec_group_override = v;
@@ -789,7 +800,9 @@ static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *
     for (uint32_t b = 0; b < nb;) {
         Chunk c{b, b, ~0ull, 0, 0, 0};
         uint64_t bytes = 0;
-        while (c.b1 < nb && (c.b1 == c.b0 || bytes + in_len[c.b1] <= kCompressChunkBytes)) {
+        // ramp: the first chunks are small (32, 64, ... MiB) so the first kernel starts after a short copy
+        const uint64_t limit = std::min<uint64_t>(kCompressChunkBytes, (32ull << 20) << std::min<size_t>(chunks.size(), 8));
+        while (c.b1 < nb && (c.b1 == c.b0 || bytes + in_len[c.b1] <= limit)) {
             const uint32_t k = c.b1++;
             c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]);
             c.in_hi = std::max<uint64_t>(c.in_hi, in_off[k] + in_len[k]);
@@ -915,7 +928,8 @@ static lz4b200_status decompress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t
         Chunk c{b, b, ~0ull, 0, ~0ull, 0};
         uint64_t bytes = 0;
         bool contig = true;
-        while (c.b1 < nb && (c.b1 == c.b0 || bytes + out_cap[c.b1] <= kChunkBytes)) {
+        const uint64_t limit = std::min<uint64_t>(kChunkBytes, (32ull << 20) << std::min<size_t>(chunks.size(), 8));
+        while (c.b1 < nb && (c.b1 == c.b0 || bytes + out_cap[c.b1] <= limit)) {
             const uint32_t k = c.b1++;
             c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]); c.in_hi = std::max<uint64_t>(c.in_hi, in_off[k] + in_len[k]);
             c.a = std::min<uint64_t>(c.a, out_off[k]); c.b = std::max<uint64_t>(c.b, out_off[k] + out_cap[k]);

@@ -335,7 +335,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             bool chk = live && cnd != kInvalid && p - cnd <= 65535u;
             bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
             uint32_t hits = __ballot_sync(kFull, hit);
-            const uint32_t terms = __ballot_sync(kFull, term);
+            const uint32_t terms = (base + 31u * stride > last_probe) ? __ballot_sync(kFull, term) : 0u;   // uniform: only near the block's end
             const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
             uint32_t same = 1u << lane;                         // lanes of this batch on my slot (incl. me)
             bool exact = w0 == 0u;

@@ -18,6 +18,12 @@
 #ifndef DEC_DEFER
 #define DEC_DEFER 1
 #endif
+#ifndef DEC_LIT_PRED
+#define DEC_LIT_PRED 0   // 1: fast-path literals as two predicated byte steps instead of a loop (A/B aid)
+#endif
+#ifndef DEC_DEFER8
+#define DEC_DEFER8 0     // 1: deferred match stores cover 8 byte steps (64 bytes for G=8) instead of 4 (A/B aid)
+#endif
 #ifndef DEC_VARIANT_A
 #define DEC_VARIANT_A 1
 #endif
@@ -364,7 +370,19 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     // measured on B200: deferral pays for 8-lane groups (4 byte-steps per match), not for wider ones
     constexpr bool kDefer = DEC_DEFER && G <= 8;
     uint8_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;                // pending match bytes of this lane
+#if DEC_DEFER8
+    uint8_t pv4 = 0, pv5 = 0, pv6 = 0, pv7 = 0;
+#endif
     uint32_t p_at = 0, p_len = 0;                              // pending match: output position, length (0 = none)
+#if DEC_DEFER8
+#define FLUSH_PENDING_HI()                                                     \
+            if (sub + 4 * G < p_len) pd[sub + 4 * G] = pv4;                    \
+            if (sub + 5 * G < p_len) pd[sub + 5 * G] = pv5;                    \
+            if (sub + 6 * G < p_len) pd[sub + 6 * G] = pv6;                    \
+            if (sub + 7 * G < p_len) pd[sub + 7 * G] = pv7;
+#else
+#define FLUSH_PENDING_HI()
+#endif
 #define FLUSH_PENDING()                                                        \
     do {                                                                       \
         if (kDefer && p_len) {                                                           \
@@ -373,6 +391,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
             if (sub + G < p_len) pd[sub + G] = pv1;                            \
             if (sub + 2 * G < p_len) pd[sub + 2 * G] = pv2;                    \
             if (sub + 3 * G < p_len) pd[sub + 3 * G] = pv3;                    \
+            FLUSH_PENDING_HI()                                                 \
             p_len = 0;                                                         \
         }                                                                      \
     } while (0)
@@ -388,6 +407,18 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                 uint32_t mlen = 4u + (v0 & 15u), adv = 2;
                 if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
                 if ((mlen != 19 + 255) && lit + mlen <= cap - op) {
+#if DEC_LIT_PRED
+                    if (G >= 8) {                              // lit <= 14 here: at most two byte steps, no loop
+                        const uint8_t *ls = src + ip + 1;
+                        uint8_t *ld = dst + op;
+                        uint8_t l0 = 0, l1 = 0;
+                        if (sub < lit) l0 = __ldg(ls + sub);
+                        if (G < 16 && sub + G < lit) l1 = __ldg(ls + sub + G);
+                        if (sub < lit) ld[sub] = l0;
+                        if (G < 16 && sub + G < lit) ld[sub + G] = l1;
+                        op += lit;
+                    } else
+#endif
                     if (lit) {
                         for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
                         op += lit;
@@ -410,12 +441,18 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                     }
                     FLUSH_PENDING();
                     __syncwarp(gmask);
-                    if (kDefer && dist >= mlen && mlen <= 4u * G) {
+                    if (kDefer && dist >= mlen && mlen <= (DEC_DEFER8 ? 8u : 4u) * G) {
                         const uint8_t *from = dst + op - dist;
                         if (sub < mlen) pv0 = from[sub];
                         if (sub + G < mlen) pv1 = from[sub + G];
                         if (sub + 2 * G < mlen) pv2 = from[sub + 2 * G];
                         if (sub + 3 * G < mlen) pv3 = from[sub + 3 * G];
+#if DEC_DEFER8
+                        if (sub + 4 * G < mlen) pv4 = from[sub + 4 * G];
+                        if (sub + 5 * G < mlen) pv5 = from[sub + 5 * G];
+                        if (sub + 6 * G < mlen) pv6 = from[sub + 6 * G];
+                        if (sub + 7 * G < mlen) pv7 = from[sub + 7 * G];
+#endif
                         p_at = op; p_len = mlen;
                     } else {
                         copy_match<G>(dst + op, dist, mlen, sub, gmask);
@@ -433,6 +470,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     }
     FLUSH_PENDING();
 #undef FLUSH_PENDING
+#undef FLUSH_PENDING_HI
     r.written = op;
     return r;
 }
@@ -595,6 +633,125 @@ lz4_decompress_blocks(BatchArgs a)
             if (a.err_expected) a.err_expected[b] = r.expected;
         }
     }
+    if (sub == 0) {
+        __threadfence();
+        if (atomicAdd(&a.tickets[1], 1u) == total_groups - 1) {
+            a.tickets[0] = 0;
+            a.tickets[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// Converged variant of the decoder (A/B: LZ4B200_DEC_CONV=1).  The plain kernel gives each lane group its own
+// block loop, so the 32/G groups of a warp drift apart and serialise (21.7 of 32 lanes active per instruction).
+// Here the warp runs ONE loop: every iteration each group decodes one sequence of its current block (or fetches a
+// new block), and a full-warp vote at the top of the loop is the reconvergence point.  Same per-sequence code,
+// same results.
+template <int G>
+__global__ void __launch_bounds__(kDecWarpsPerCta * 32)
+lz4_decompress_blocks_conv(BatchArgs a)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane & (G - 1), leader = lane & ~uint32_t(G - 1);
+    const uint32_t gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << leader);
+    const uint32_t total_groups = gridDim.x * kDecWarpsPerCta * (32 / G);
+    const uint8_t *__restrict__ src = nullptr;
+    uint8_t *dst = nullptr;
+    const uint32_t *vw = nullptr;
+    uint32_t vmis = 0, n = 0, cap = 0, ip = 0, op = 0, b = 0;
+    bool have = false, dry = false;
+    DecResult r{0u, LZ4B200_OK, 0ull};
+    uint8_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0;                // pending (deferred) match bytes of this lane
+    uint32_t p_at = 0, p_len = 0;
+#define CONV_FLUSH()                                                           \
+    do {                                                                       \
+        if (p_len) {                                                           \
+            uint8_t *pd = dst + p_at;                                          \
+            if (sub < p_len) pd[sub] = pv0;                                    \
+            if (sub + G < p_len) pd[sub + G] = pv1;                            \
+            if (sub + 2 * G < p_len) pd[sub + 2 * G] = pv2;                    \
+            if (sub + 3 * G < p_len) pd[sub + 3 * G] = pv3;                    \
+            p_len = 0;                                                         \
+        }                                                                      \
+    } while (0)
+    for (;;) {
+        if (!have && !dry) {
+            if (sub == 0) b = atomicAdd(&a.tickets[0], 1u);
+            b = __shfl_sync(gmask, b, leader);
+            if (b >= a.nblocks) {
+                dry = true;
+            } else {
+                src = a.in + a.in_off[b]; n = a.in_len[b]; dst = a.out + a.out_off[b]; cap = a.out_cap[b];
+                vw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~uintptr_t(3));
+                vmis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+                ip = 0; op = 0; p_len = 0;
+                r.written = 0; r.status = LZ4B200_OK; r.expected = 0;
+                have = true;
+            }
+        }
+        if (__all_sync(kFull, dry)) break;                      // the warp's reconvergence point
+        if (!have) continue;
+        int fin = 0;                                            // 0 = go on, 1 = block finished, 2 = error
+        if (n == 0) { r.status = LZ4B200_DEC_EXPECTED_ANOTHER_BYTE; fin = 2; }   // decompress.rs:207-209
+        bool fast = false;
+        if (!fin && ip + 8 <= n) {
+            uint32_t x = ip + vmis;
+            const uint32_t v0 = __funnelshift_r(__ldg(vw + (x >> 2)), __ldg(vw + (x >> 2) + 1), (x & 3u) * 8u);
+            const uint32_t lit = (v0 >> 4) & 15u;
+            const uint32_t q = ip + 1 + lit;
+            if (lit != 15 && q + 8 <= n) {
+                uint32_t v1 = v0 >> 8;
+                if (lit) {
+                    x = q + vmis;
+                    v1 = __funnelshift_r(__ldg(vw + (x >> 2)), __ldg(vw + (x >> 2) + 1), (x & 3u) * 8u);
+                }
+                const uint32_t dist = v1 & 0xffffu;
+                uint32_t mlen = 4u + (v0 & 15u), adv = 2;
+                if (mlen == 19) { mlen += (v1 >> 16) & 0xffu; adv = 3; }
+                if ((mlen != 19 + 255) && lit + mlen <= cap - op) {
+                    fast = true;
+                    if (lit) {
+                        for (uint32_t i = sub; i < lit; i += G) dst[op + i] = __ldg(src + ip + 1 + i);
+                        op += lit;
+                    }
+                    if (dist == 0) { r.status = LZ4B200_DEC_OFFSET_ZERO; fin = 2; }
+                    else if (dist > op) { r.status = LZ4B200_DEC_OFFSET_OUT_OF_BOUNDS; fin = 2; }
+                    else {
+                        CONV_FLUSH();
+                        __syncwarp(gmask);
+                        if (G <= 8 && dist >= mlen && mlen <= 4u * G) {
+                            const uint8_t *from = dst + op - dist;
+                            if (sub < mlen) pv0 = from[sub];
+                            if (sub + G < mlen) pv1 = from[sub + G];
+                            if (sub + 2 * G < mlen) pv2 = from[sub + 2 * G];
+                            if (sub + 3 * G < mlen) pv3 = from[sub + 3 * G];
+                            p_at = op; p_len = mlen;
+                        } else {
+                            copy_match<G>(dst + op, dist, mlen, sub, gmask);
+                        }
+                        op += mlen;
+                        ip = q + adv;                           // < n because q + 8 <= n
+                    }
+                }
+            }
+        }
+        if (!fin && !fast) {
+            CONV_FLUSH();
+            const int c = decode_sequence_checked<G>(src, n, dst, cap, ip, op, sub, gmask, r);
+            if (c == 1) { r.written = op; fin = 1; }
+            else if (c == 2) fin = 2;
+        }
+        if (fin) {
+            if (sub == 0) {
+                a.out_len[b] = r.status == LZ4B200_OK ? r.written : 0u;
+                a.status[b] = r.status;
+                if (a.err_expected) a.err_expected[b] = r.expected;
+            }
+            have = false;
+        }
+    }
+#undef CONV_FLUSH
     if (sub == 0) {
         __threadfence();
         if (atomicAdd(&a.tickets[1], 1u) == total_groups - 1) {

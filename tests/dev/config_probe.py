@@ -2,7 +2,7 @@
 config 3: decompress-only, dickens.txt tiled to 1 GiB of 64 KiB blocks (oracle-compressed).
 config 5: 64 KiB all-zero blocks and incompressible blocks interleaved, zero fraction sweep."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import oracle
 from lz4_flex_b200 import block, corpus

@@ -1,6 +1,6 @@
 """Development aid (run under gpurun): host-batch call timings for chunk-size / overlap tuning."""
 import os, sys, time, threading, queue
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from lz4_flex_b200 import block, corpus
 nb = 16384; B = 65536

@@ -1,6 +1,6 @@
 """Ad-hoc GPU parity sweep (run under gpurun during development); the real tests are test_gpu_*.py."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from lz4_flex_b200 import block, corpus, frame
