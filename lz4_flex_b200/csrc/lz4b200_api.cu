@@ -369,7 +369,7 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             // global-table encoder: 8 warps per CTA, 8 CTAs per SM
             const int m = ctx->enc_gtab / 10, e = ctx->enc_gtab % 10;
             want = (a.nblocks + m - 1) / m;
-            grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 8u);
+            grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * (m == 15 ? 4u : 8u));
             // one table region per concurrently running launch (the host pipeline launches from up to 8 lanes):
             // the ticket block doubles as the region selector
             const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;             // u16 entries
@@ -384,7 +384,8 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
                                      ctx->enc_gtab_carveout);
                 ctx->enc_gtab_carveout_set = true;
             }
-            if (m == 6 && e == 2) lz4_compress_blocks_gtab<uint16_t, 6, 2, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            if (m == 15) lz4_compress_blocks_gtab<uint16_t, 15, 1, 0><<<grid, 512, 0, s>>>(a, tickets + 2, gt);
+            else if (m == 6 && e == 2) lz4_compress_blocks_gtab<uint16_t, 6, 2, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else if (m == 4 && e == 4) lz4_compress_blocks_gtab<uint16_t, 4, 4, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else if (ks == 2) lz4_compress_blocks_gtab<uint16_t, 7, 1, 2><<<grid, 256, 2 * 8192, s>>>(a, tickets + 2, gt);
             else if (ks == 3) {

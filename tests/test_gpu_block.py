@@ -314,3 +314,25 @@ def test_config5_adversarial(ctx):
         back = np.zeros(nb * B, dtype=np.uint8)
         block.decompress_batch(out, ooff, olen, back, offs, lens, ctx)
         assert np.array_equal(back, data)
+
+
+def test_host_batch_many_small_blocks_global_table_path(ctx):
+    """More blocks per launch than the shared-memory-table kernel keeps in flight (24 per SM): the launcher picks the
+    global-table kernel, here from two pipeline lanes at once (each lane owns its own table region).  Ragged block
+    lengths around the interesting sizes; bytes identical to the oracle, exact round trip."""
+    src = corpus.tiled("compression_66k_JSON.txt", 48 << 20)
+    rng = np.random.default_rng(21)
+    lens = rng.integers(1500, 3000, 20000).astype(np.uint32)
+    lens[:64] = np.arange(64, dtype=np.uint32)                        # 0..63: tiny blocks, the n < 13 path included
+    offs = np.zeros(lens.size, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    assert int(offs[-1]) + int(lens[-1]) <= src.size
+    out, ooff, olen = block.compress_batch(src, offs, lens, ctx=ctx)
+    for b in list(range(0, 64)) + list(range(64, lens.size, 397)) + [lens.size - 1]:
+        a, n = int(offs[b]), int(lens[b])
+        got = out[int(ooff[b]): int(ooff[b]) + int(olen[b])].tobytes()
+        assert got == oracle.compress_block(src[a: a + n].tobytes()), b
+    back = np.zeros(int(offs[-1]) + int(lens[-1]), dtype=np.uint8)
+    ol, st, _ = block.decompress_batch(out, ooff, olen, back, offs, lens, ctx=ctx)
+    assert not st.any() and np.array_equal(ol, lens)
+    assert np.array_equal(back, src[: back.size])
