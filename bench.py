@@ -48,18 +48,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in-process at
+    ~2 ms intervals (the timed region of the default run lasts ~0.25 s, too short for an `nvidia-smi -lms` loop to
+    deliver samples); falls back to the nvidia-smi loop when pynvml is unavailable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.samples = []           # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.nvml, self.handle = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n, h = self.nvml, self.handle
+        while not self._stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+                try:
+                    why = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    why = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -74,6 +117,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            sm = [s[0] for s in self.samples]
+            mask = 0
+            for _, w in self.samples:
+                mask |= w
+            reasons = sorted(nm for bit, nm in self.BITS.items() if mask & bit)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +148,7 @@ class ClockSampler:
                 if f[5 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def ncu_traffic(prefix: str):
