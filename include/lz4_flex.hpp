@@ -168,6 +168,27 @@ inline Result<std::vector<uint8_t>, DecompressError> decompress_size_prepended(c
     return decompress(s.value().second, n - 4, s.value().first, ctx);
 }
 
+// block::CompressTable / compress_into_with_table (compress.rs:709-766)
+struct CompressTable {
+    enum Kind { Small = LZ4B200_TABLE_SMALL, Large = LZ4B200_TABLE_LARGE } kind = Small;
+    static CompressTable small() { return CompressTable{Small}; }
+    static CompressTable large() { return CompressTable{Large}; }
+};
+
+inline Result<size_t, CompressError> compress_into_with_table(const uint8_t *input, size_t n, uint8_t *output, size_t cap,
+                                                              CompressTable &table, lz4b200_ctx *ctx = nullptr)
+{
+    using R = Result<size_t, CompressError>;
+    if (!ctx) ctx = default_context();
+    if (!ctx) return R::Err({CompressError::Cuda});
+    size_t written = 0;
+    int kind = (int)table.kind;
+    const lz4b200_status st = lz4b200_compress_into_with_table(ctx, input, n, output, cap, &written, &kind);
+    table.kind = (CompressTable::Kind)kind;
+    if (st == LZ4B200_OK) return R::Ok(written);
+    return R::Err({st == LZ4B200_COMPRESS_OUTPUT_TOO_SMALL ? CompressError::OutputTooSmall : CompressError::Cuda});
+}
+
 // ---- external dictionary (compress.rs:610-616, 685-694; decompress.rs:462-468, 478-528) ----
 
 // block::compress_into_with_dict (compress.rs:610)

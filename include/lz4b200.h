@@ -176,6 +176,15 @@ lz4b200_status lz4b200_decompress_batch_host(lz4b200_ctx *ctx,
     uint8_t *out, const uint64_t *out_off, const uint32_t *out_cap,
     uint32_t *out_len, int32_t *status, uint64_t *err_expected, size_t nblocks);
 
+/* block::compress_into_with_table — src/block/compress.rs:744-766, CompressTable :709-735.  The reusable table
+ * only selects the table layout / hash of the parse: LZ4B200_TABLE_SMALL = u16 entries + 4-byte hash (inputs
+ * < 65 535 bytes), LZ4B200_TABLE_LARGE = u32 entries + 5-byte hash (any size).  A SMALL table given an input of
+ * >= 65 535 bytes is upgraded to LARGE and stays LARGE (compress.rs:750-752): *table_kind is that in/out state. */
+#define LZ4B200_TABLE_SMALL 0
+#define LZ4B200_TABLE_LARGE 1
+lz4b200_status lz4b200_compress_into_with_table(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                                uint8_t *out, size_t cap, size_t *written, int *table_kind);
+
 /* ---- external dictionary ("_with_dict") -----------------------------------------------------
  * The dictionary logically precedes the input: the encoder may reference its last 64 KiB, the decoder
  * resolves offsets that reach before the start of the output inside it.  Like the reference, the

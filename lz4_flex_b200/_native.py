@@ -85,6 +85,7 @@ SIGNATURES = {
     "lz4b200_decompress_batch_device": (_i32, [_vp] * 10 + [_sz, _vp]),
     "lz4b200_compress_batch_host": (_i32, [_vp] * 6 + [_sz] + [_vp] * 3 + [_sz]),
     "lz4b200_decompress_batch_host": (_i32, [_vp] * 10 + [_sz]),
+    "lz4b200_compress_into_with_table": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(C.c_int)]),
     "lz4b200_compress_into_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz]),
     "lz4b200_compress_prepend_size_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz]),
     "lz4b200_decompress_into_with_dict": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp, _sz, _psz, _psz, _psz]),

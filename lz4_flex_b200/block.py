@@ -186,6 +186,41 @@ def decompress_size_prepended(input, ctx: Context | None = None) -> bytes:
     return decompress(rest, size, ctx)
 
 
+# ---- reusable table ---------------------------------------------------------------------------------------
+
+class CompressTable:
+    """block::CompressTable (compress.rs:709-735): Small (u16 entries, 4-byte hash, inputs < 65 535 bytes) or Large
+    (u32 entries, 5-byte hash, any size).  The table's memory lives on the GPU; this object carries the variant, which
+    is what decides the bytes produced."""
+    SMALL, LARGE = 0, 1
+
+    def __init__(self, kind: int = 0):
+        self.kind = kind
+
+    @classmethod
+    def small(cls) -> "CompressTable":
+        return cls(cls.SMALL)
+
+    @classmethod
+    def large(cls) -> "CompressTable":
+        return cls(cls.LARGE)
+
+
+def compress_into_with_table(input, output, table: CompressTable, ctx: Context | None = None) -> int:
+    """block::compress_into_with_table (compress.rs:744-766).  A Small table handed an input of >= 65 535 bytes is
+    upgraded to Large and stays Large."""
+    ctx = ctx or default_context()
+    src = _as_u8(input)
+    dst = _as_u8(output) if isinstance(output, np.ndarray) else np.frombuffer(output, dtype=np.uint8)
+    w, k = C.c_size_t(0), C.c_int(table.kind)
+    st = _native.lib().lz4b200_compress_into_with_table(ctx.handle, _ptr(src), src.size, _ptr(dst), dst.size,
+                                                        C.byref(w), C.byref(k))
+    table.kind = k.value
+    if st != 0:
+        _raise(ctx, st)
+    return w.value
+
+
 # ---- external dictionary ------------------------------------------------------------------------------
 
 def compress_into_with_dict(input, output, dict_data, ctx: Context | None = None) -> int:

@@ -1116,6 +1116,31 @@ lz4b200_status lz4b200_compress_into_with_dict(lz4b200_ctx *ctx, const uint8_t *
     return LZ4B200_OK;
 }
 
+// block::compress_into_with_table (compress.rs:744-766).  The reusable CompressTable only decides which table
+// layout / hash the parse uses: Small = u16 entries + 4-byte hash (inputs < 65 535 bytes), Large = u32 entries +
+// 5-byte hash for any size; a Small table handed an input >= 65 535 bytes is upgraded to Large and stays Large.
+// *table_kind carries that state (LZ4B200_TABLE_SMALL / LZ4B200_TABLE_LARGE); the table's memory lives on the GPU.
+lz4b200_status lz4b200_compress_into_with_table(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                                size_t *written, int *table_kind)
+{
+    if (!ctx || !written || !table_kind || (!in && n) || n > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
+    if (*table_kind != LZ4B200_TABLE_SMALL && *table_kind != LZ4B200_TABLE_LARGE) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0;
+    if (n >= 65535 && *table_kind == LZ4B200_TABLE_SMALL) *table_kind = LZ4B200_TABLE_LARGE;      // compress.rs:750-752
+    if (cap < lz4b200_max_output_size(n)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;                // compress.rs:338-340
+    uint64_t in_off = 0, out_off = 0;
+    uint32_t in_len = (uint32_t)n, out_len = 0;
+    int32_t status = 0;
+    const uint8_t flag = *table_kind == LZ4B200_TABLE_LARGE ? (uint8_t)LZ4B200_BLOCK_HASH5_ALWAYS : (uint8_t)0;
+    static const uint8_t zero = 0;
+    lz4b200_status st = compress_batch_host_impl(ctx, n ? in : &zero, &in_off, &in_len, &flag, nullptr, 0, out, cap,
+                                                 &out_off, &out_len, &status, 1);
+    if (st != LZ4B200_OK) return st;
+    if (status != LZ4B200_OK) return (lz4b200_status)status;
+    *written = out_len;
+    return LZ4B200_OK;
+}
+
 lz4b200_status lz4b200_compress_prepend_size_with_dict(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
                                                        const uint8_t *dict, size_t dict_len, uint8_t *out, size_t cap,
                                                        size_t *written)

@@ -96,3 +96,24 @@ def test_dict_batch_shared_dictionary(ctx):
     outs, status, _ = block.decompress_blocks_with_dict(comp, [max(len(b), 1) for b in blocks], dct, ctx)
     assert not status.any()
     assert all(o == b for o, b in zip(outs, blocks))
+
+
+def test_compress_into_with_table(ctx):
+    """block::compress_into_with_table (compress.rs:744-766): the table variant selects the hash; a Small table handed an
+    input of >= 65 535 bytes becomes Large and stays Large."""
+    small_in = corpus.load("compression_34k.txt")
+    big_in = corpus.load("compression_66k_JSON.txt")
+    out = np.zeros(block.get_maximum_output_size(len(big_in)), dtype=np.uint8)
+    t = block.CompressTable.small()
+    n = block.compress_into_with_table(small_in, out, t, ctx)
+    assert out[:n].tobytes() == oracle.compress_block(small_in) and t.kind == block.CompressTable.SMALL
+    n = block.compress_into_with_table(big_in, out, t, ctx)                 # upgrade
+    assert out[:n].tobytes() == oracle.compress_block(big_in) and t.kind == block.CompressTable.LARGE
+    n = block.compress_into_with_table(small_in, out, t, ctx)               # stays Large: 5-byte hash on a small input
+    assert out[:n].tobytes() == oracle.compress_block_fresh_h5(small_in)
+    assert out[:n].tobytes() != oracle.compress_block(small_in)
+    t2 = block.CompressTable.large()
+    n = block.compress_into_with_table(b"", out, t2, ctx)
+    assert out[:n].tobytes() == oracle.compress_block(b"")
+    with pytest.raises(errors.CompressOutputTooSmall):
+        block.compress_into_with_table(small_in, np.zeros(10, dtype=np.uint8), t2, ctx)
