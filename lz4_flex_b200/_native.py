@@ -43,12 +43,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found and liblz4b200.so is missing or stale")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + _sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    # several ranks of one torchrun job may get here at once: one builds (under a file lock, into a temporary that
+    # is renamed into place), the others wait and find a fresh library
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return SO_PATH
+            tmp = f"{SO_PATH}.tmp{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 

@@ -208,3 +208,15 @@ def test_linked_frame_errors_match_oracle(ctx):
             assert type(err) is type(want_err), (t, st, berr, err)
             if isinstance(err, errors.DecompressionError):
                 assert type(err.inner) is type(want_err.inner), (t, berr, err.inner)
+
+
+def test_large_64k_block_frame_uses_global_table_encoder(ctx):
+    """A frame of 3 800 x 64 KiB blocks: more blocks in one launch than the shared-memory-table encoder keeps in flight,
+    so the frame path runs the global-table kernel — here with CONT-mode blocks (every block but the first continues the
+    frame's table epoch).  Byte-identical to the oracle frame; round trip exact."""
+    import hashlib
+    data = corpus.tiled("compression_66k_JSON.txt", 3800 * 65536)
+    f = frame.compress_frame(data, frame.FrameInfo(block_size=frame.BlockSize.Max64KB, content_checksum=True), ctx=ctx)
+    want = oracle.frame_compress(data.tobytes(), 4, oracle.F_CONTENT_CHECKSUM)
+    assert len(f) == len(want) and hashlib.sha256(f).digest() == hashlib.sha256(want).digest()
+    assert frame.decompress_frame(f, ctx=ctx) == data.tobytes()
