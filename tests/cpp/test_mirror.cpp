@@ -71,6 +71,38 @@ int main(int argc, char **argv)
         auto ez = block::decompress_into(v2, 0, o, 3);
         CHECK(ez.is_err() && ez.error().kind == block::DecompressError::ExpectedAnotherByte);
     }
+    // ---- dictionary and reusable-table API (compress.rs:610-616, 685-694, 744-766; decompress.rs:462-528) ----
+    {
+        const uint8_t in[] = {10, 12, 14, 16, 18, 10, 12, 14, 16, 18, 10, 12, 14, 16, 18, 10, 12, 14, 16, 18};   // compress.rs:892-911
+        auto plain = block::compress(in, sizeof in);
+        auto with = block::compress_with_dict(in, sizeof in, in, sizeof in);
+        CHECK(!with.empty() && with.size() < plain.size());
+        auto rt = block::decompress_with_dict(with.data(), with.size(), sizeof in, in, sizeof in);
+        CHECK(rt.is_ok() && rt.value() == std::vector<uint8_t>(in, in + sizeof in));
+        const uint8_t tiny[] = {10, 12, 14};                                                      // compress.rs:913-919
+        CHECK(block::compress_with_dict(in, sizeof in, tiny, 3) == plain);
+        auto p = block::compress_prepend_size_with_dict(d.data() + 100000, 50000, d.data(), 100000);
+        auto q = block::decompress_size_prepended_with_dict(p.data(), p.size(), d.data(), 100000);
+        CHECK(q.is_ok() && q.value() == std::vector<uint8_t>(d.begin() + 100000, d.begin() + 150000));
+        CHECK(p.size() < block::compress_prepend_size(d.data() + 100000, 50000).size());
+        const uint8_t oob[] = {0x0E, 255, 0, 0x70, 0, 0, 0, 0, 0, 0, 0};                          // decompress.rs:593-601
+        std::vector<uint8_t> zeros(250, 0);
+        auto e = block::decompress_with_dict(oob, sizeof oob, 256, zeros.data(), zeros.size());
+        CHECK(e.is_err() && e.error().kind == block::DecompressError::OffsetOutOfBounds);
+        // CompressTable: a Small table is upgraded by an input >= 65 535 bytes and stays Large (5-byte hash)
+        block::CompressTable t = block::CompressTable::small();
+        std::vector<uint8_t> o1(block::get_maximum_output_size(d.size())), o2(o1.size());
+        auto a = block::compress_into_with_table(d.data(), 30000, o1.data(), o1.size(), t);
+        CHECK(a.is_ok() && t.kind == block::CompressTable::Small);
+        auto ref30k = block::compress(d.data(), 30000);
+        CHECK(a.is_ok() && std::vector<uint8_t>(o1.begin(), o1.begin() + a.value()) == ref30k);
+        auto b = block::compress_into_with_table(d.data(), 70000, o2.data(), o2.size(), t);
+        CHECK(b.is_ok() && t.kind == block::CompressTable::Large);
+        auto c2 = block::compress_into_with_table(d.data(), 30000, o2.data(), o2.size(), t);
+        CHECK(c2.is_ok() && t.kind == block::CompressTable::Large);
+        auto back30k = block::decompress(o2.data(), c2.value(), 30000);
+        CHECK(back30k.is_ok() && back30k.value() == std::vector<uint8_t>(d.begin(), d.begin() + 30000));
+    }
     // ---- frame API: chunked writes through FrameEncoder == one-shot C call ----------------------
     for (int variant = 0; variant < 3; variant++) {
         frame::FrameInfo info;

@@ -1,3 +1,3 @@
 #!/bin/bash
 # development aid (run under gpurun)
-timeout 600 python -m pytest tests/test_gpu_frame.py -x -q 2>&1 | tail -4
+timeout 600 python -m pytest tests/test_cpp_mirror.py -m gpu -x -q 2>&1 | tail -6
