@@ -1,4 +1,8 @@
-// lz4b200_enc_split.cuh — K1 as a two-warp pipeline per block (included by lz4b200_kernels.cuh).
+// lz4b200_enc_split.cuh — K1 as a matcher/emitter warp pipeline (included by lz4b200_kernels.cuh).
+//
+// Two kernels share the code below: lz4_compress_blocks_split (one emitter per matcher, tables in shared memory,
+// 24 matchers per SM) and lz4_compress_blocks_gtab (7 matchers per emitter, tables in global memory served by
+// L2, 56 matchers per SM).  The launcher picks by batch size.
 //
 // compress_internal (reference src/block/compress.rs:318-489) does two things per sequence: it SEARCHES
 // (probe loop :373-439, backward/forward extension :272-287 / :156-216, the cur-2 re-insert :460-461) and it
@@ -6,12 +10,13 @@
 // probe starts where this match ends — while emission depends on nothing but the finished
 // (anchor, match start, offset, match end) tuple.  So a block is handled by a PAIR of warps:
 //
-//   matcher warp : owns the 4096-slot table in shared memory and runs the exact emulation of the sequential
-//                  probe loop (32 probes per batch, in-batch table forwarding with match.any); it pushes one
-//                  16-byte tuple per sequence into a shared-memory ring and goes straight on to the next probe.
+//   matcher warp : owns the block's 4096-slot table and runs the exact emulation of the sequential probe loop
+//                  (32 probes per batch, speculative pre-batch candidates, in-batch table forwarding with
+//                  shuffles / match.any only when slots collide); it pushes one 16-byte tuple per sequence into a
+//                  shared-memory ring and goes straight on to the next probe.
 //   emitter warp : takes a batch of tuples at a time, one per lane; every lane sizes its own sequence, a warp
 //                  exclusive scan (__shfl_up) turns sizes into output offsets, and the lanes write token /
-//                  length bytes / literals / offset of 32 sequences at once (long literal runs are copied by the
+//                  length bytes / literals / offset of the whole batch at once (long literal runs are copied by the
 //                  whole warp).  This is the scan-compacted emission the north star asks for, and it takes
 //                  ~27 % of the per-sequence chain off the matcher.
 //

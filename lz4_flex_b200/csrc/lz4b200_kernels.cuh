@@ -1,11 +1,13 @@
 // lz4b200_kernels.cuh — sm_100a device code of the LZ4 block codec.
 //
-// K2  lz4_decompress_blocks : decompress_internal  (reference src/block/decompress.rs:201-449)
-// K1  lz4_compress_blocks   : compress_internal    (reference src/block/compress.rs:318-489)
+// K2  lz4_decompress_blocks (+ _linked, _conv)  : decompress_internal  (reference src/block/decompress.rs:201-449)
+// K1  lz4_compress_blocks (single warp per block; A/B fallback)     : compress_internal (src/block/compress.rs:318-489)
+//     The production encoders — matcher/emitter warp pipelines with shared-memory or global-memory tables —
+//     live in lz4b200_enc_split.cuh, included at the end of this file.
 //
-// Both kernels are persistent: a fixed grid of warps pulls block indices from a global ticket
-// counter, one LZ4 block per warp at a time.  This is HBM/L2-bound byte shuffling — no tensor
-// cores.  See DESIGN.md for the layout, the per-kernel roofline and what each phase costs.
+// All kernels are persistent: a fixed grid of warps pulls block indices from a global ticket
+// counter.  This is latency-bound byte shuffling — no tensor cores.  See DESIGN.md for the layout,
+// the per-kernel roofline and what each phase costs.
 #pragma once
 // Build-time variant switches (A/B-measured on B200).
 // ENC_SPLIT=1: matcher warp + emitter warp per block (lz4_compress_blocks_split); 0: one warp does both (v1).
