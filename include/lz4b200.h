@@ -136,7 +136,9 @@ lz4b200_status lz4b200_decompress_size_prepended(lz4b200_ctx *ctx, const uint8_t
 /* ---- block API, many independent blocks, DEVICE pointers (the measured hot path) ----------
  * Block b reads  d_in  + in_off[b]  (in_len[b] bytes)
  *       writes   d_out + out_off[b] (at most out_cap[b] bytes; out_len[b] = bytes produced)
- * All descriptor arrays live in device memory.  Work is enqueued on `stream`.
+ * All descriptor arrays live in device memory.  Work is enqueued on `stream`.  A context carries the
+ * work-distribution counters (and the encoder's global hash tables) of ONE batch call at a time: calls on the same
+ * context must be stream-ordered; use one context per concurrently running stream or host thread.
  * Per-block results: d_status[b] (lz4b200_status) and, for decode, d_err_expected[b]
  * (the `expected` of OutputTooSmall; `actual` is out_cap[b]).  A failed block never disturbs
  * its neighbours. */
