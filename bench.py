@@ -209,6 +209,40 @@ def cpu_arm(data: np.ndarray, nblocks: int, threads: int, repeats: int):
             "ratio": float(clen.astype(np.uint64).sum()) / (nblocks * BLOCK)}
 
 
+def liblz4_anchor(data: np.ndarray, nblocks: int):
+    """Sanity anchor: system liblz4 (LZ4_compress_default / LZ4_decompress_safe), one thread, same
+    blocks.  lz4_flex's README puts its unsafe path within ~10 % of C lz4.  Returns None when liblz4 is absent."""
+    import ctypes
+    try:
+        L = ctypes.CDLL("liblz4.so.1")
+    except OSError:
+        return None
+    L.LZ4_compress_default.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.LZ4_decompress_safe.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.LZ4_compressBound.argtypes = [ctypes.c_int]
+    bound = L.LZ4_compressBound(BLOCK)
+    comp = np.zeros(nblocks * bound, dtype=np.uint8)
+    back = np.zeros(nblocks * BLOCK, dtype=np.uint8)
+    clen = np.zeros(nblocks, dtype=np.int64)
+    comp[::4096] = 1; back[::4096] = 1                       # pre-fault
+    src, dst, bk = data.ctypes.data, comp.ctypes.data, back.ctypes.data
+    best_c = best_d = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        for b in range(nblocks):
+            clen[b] = L.LZ4_compress_default(src + b * BLOCK, dst + b * bound, BLOCK, bound)
+        t1 = time.perf_counter()
+        for b in range(nblocks):
+            L.LZ4_decompress_safe(dst + b * bound, bk + b * BLOCK, int(clen[b]), BLOCK)
+        t2 = time.perf_counter()
+        best_c, best_d = min(best_c, t1 - t0), min(best_d, t2 - t1)
+    if not np.array_equal(back, data[: nblocks * BLOCK]):
+        return None
+    mib = nblocks * BLOCK / 2**20
+    return {"library": "liblz4 (system)", "threads": 1, "compress_mibs": mib / best_c, "decompress_mibs": mib / best_d,
+            "ratio": float(clen.sum()) / (nblocks * BLOCK)}
+
+
 def run_reference(args):
     """Reference arm: the CPU implementation of the path on all host cores (oracle port; no Rust toolchain)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -465,7 +499,8 @@ def run_ours(args):
                       f"{threads} threads (one block per task)",
             "compress_mibs": cpu_all["compress_mibs"], "decompress_mibs": cpu_all["decompress_mibs"],
             "single_thread": {"compress_mibs": cpu_one["compress_mibs"],
-                              "decompress_mibs": cpu_one["decompress_mibs"]}},
+                              "decompress_mibs": cpu_one["decompress_mibs"]},
+            "liblz4_anchor": liblz4_anchor(data, min(nb, 512))},
         "e2e": {"value": world * mib_rank / e2e_s, "unit": "MiB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
                 "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks,
