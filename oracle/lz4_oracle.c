@@ -16,7 +16,10 @@
  *   - the frame header known bytes (fuzz/fuzz_targets/fuzz_decomp_corrupt_frame.rs:26-27),
  *   - the legacy-frame fixture benches/dickens.lz4 (tests/tests.rs:741-745),
  *   - cross-decoding by the system liblz4 1.9.4 (the reference's own interop check,
- *     tests/tests.rs:109-147).
+ *     tests/tests.rs:109-147), including LZ4_decompress_safe_usingDict for the dictionary
+ *     encoder and LZ4F-written linked-block frames for the frame decoder,
+ *   - the reference's dictionary unit tests (src/block/compress.rs:892-950,
+ *     src/block/decompress.rs:593-601).
  * COMPRESSED BYTES are not pinned by any reference fixture ("parity unpinned" for the
  * exact encoder output): the known-answers in tests/golden/ come
  * from two independent restatements agreeing (this file and the surveyor's), not from
@@ -29,6 +32,10 @@
  *   lz4o_compress_block()    src/block/compress.rs:554-567  (table/hash choice), :599
  *   lz4o_decompress_block()  src/block/decompress.rs:201-449 (error order), cross-read with
  *                            src/block/decompress_safe.rs:93-247
+ *   lz4o_compress_block_dict()   src/block/compress.rs:554-583 (table choice, init_dict), :412-421 (ext_dict
+ *                            candidates), :156-216 / :272-287 (extension confined to the candidate's source)
+ *   lz4o_decompress_block_dict() src/block/decompress.rs:85-109 (copy_from_dict), :287-301, :399-427
+ *   linked frames (decode)   src/frame/decompress.rs:196-222, 277-305
  *   lz4o_xxh32()             twox-hash 2.x XxHash32 (Cargo.toml:51) = standard XXH32
  *   lz4o_frame_*()           src/frame/header.rs:232-372, :383-410;
  *                            src/frame/compress.rs:234-371; src/frame/decompress.rs:109-342
