@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "lz4b200_kernels.cuh"
+#include "lz4b200_thread_kernels.cuh"
 
 using namespace lz4b200;
 
@@ -259,6 +260,7 @@ struct lz4b200_ctx {
     int enc_gtab_carveout = -1;               // LZ4B200_ENC_GTAB_CARVEOUT=<percent of shared memory>
     bool enc_gtab_carveout_set = false;
     DevBuf<uint16_t> d_gtab16;
+    DevBuf<uint16_t> d_ttab16;                // K1-T tables
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
     int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
@@ -266,6 +268,12 @@ struct lz4b200_ctx {
     int dec_conv = 0;                         // LZ4B200_DEC_CONV=1: warp-converged decoder loop (A/B aid)
     int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
     int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32 (tuning aid)
+    // K1-T / K2-T (one block per thread, lz4b200_thread_kernels.cuh): used for batches of at least thread_min_blocks
+    // blocks of <= 64 KiB without a dictionary.  LZ4B200_THREAD_MIN / _ENC_THREAD_LANES / _DEC_THREAD_LANES /
+    // _ENC_THREADS / _DEC_THREADS override the launch shape (tuning aids).
+    uint32_t enc_thread_min = 4096, dec_thread_min = 4096;
+    int enc_thread_lanes = 0, dec_thread_lanes = 0;   // 0: chosen from the batch size
+    uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
     std::string last_error;
 
     // scratch for host-pointer and frame entry points
@@ -333,11 +341,38 @@ int pick_dec_group(const lz4b200_ctx *ctx, uint32_t nblocks)
     return nblocks >= 4096 ? 16 : 32;
 }
 
+// Active lanes per warp for the thread-per-block kernels: a batch with fewer blocks than the GPU has lanes is
+// spread over more warps.
+int pick_thread_lanes(const lz4b200_ctx *ctx, uint32_t threads, int override_lanes)
+{
+    if (override_lanes == 8 || override_lanes == 16 || override_lanes == 32) return override_lanes;
+    const uint32_t full = (uint32_t)ctx->sm_count * 64u * 32u;      // every lane of every resident warp
+    if (threads * 4u <= full) return 8;
+    return threads * 2u <= full ? 16 : 32;
+}
+
+template <int kLanes>
+lz4b200_status launch_decompress_thread(lz4b200_ctx *ctx, const BatchArgs &a, uint32_t threads, cudaStream_t s)
+{
+    const uint32_t per_cta = kThreadCtaWarps * kLanes;
+    lz4_decompress_blocks_thread<kLanes><<<(threads + per_cta - 1) / per_cta, kThreadCtaWarps * 32, 0, s>>>(a);
+    CTX_CUDA(ctx, cudaGetLastError());
+    return LZ4B200_OK;
+}
+
 lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s, uint32_t *tickets = nullptr)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     a.tickets = tickets ? tickets : ctx->d_tickets;
+    if (!a.dict_len && a.nblocks >= ctx->dec_thread_min) {
+        const uint32_t threads = std::min(a.nblocks, ctx->dec_thread_max);
+        switch (pick_thread_lanes(ctx, threads, ctx->dec_thread_lanes)) {
+        case 8: return launch_decompress_thread<8>(ctx, a, threads, s);
+        case 16: return launch_decompress_thread<16>(ctx, a, threads, s);
+        default: return launch_decompress_thread<32>(ctx, a, threads, s);
+        }
+    }
     switch (pick_dec_group(ctx, a.nblocks)) {
     case 4: return launch_decompress_g<4>(ctx, a, s);
     case 8: return launch_decompress_g<8>(ctx, a, s);
@@ -352,6 +387,21 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     if (!tickets) tickets = ctx->d_tickets;
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
+    if (!a.dict_len && max_in_len != 0 && max_in_len <= 65536u && a.nblocks >= ctx->enc_thread_min) {
+        // K1-T: one block per thread, 8 KiB table per thread in global memory (one region per concurrent launch)
+        const uint32_t threads = std::min(a.nblocks, ctx->enc_thread_max);
+        const size_t region = (size_t)ctx->enc_thread_max * 4096u;                  // u16 entries
+        const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
+        if (!ctx->check(ctx->d_ttab16.reserve(region * (slot ? 9u : 1u)), "thread tables")) return LZ4B200_CUDA_ERROR;
+        uint16_t *gt = ctx->d_ttab16.p + slot * region;
+        const int lanes = pick_thread_lanes(ctx, threads, ctx->enc_thread_lanes);
+        const uint32_t per_cta = kThreadCtaWarps * lanes, grid = (threads + per_cta - 1) / per_cta;
+        if (lanes == 8) lz4_compress_blocks_thread<8><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
+        else if (lanes == 16) lz4_compress_blocks_thread<16><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
+        else lz4_compress_blocks_thread<32><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
+        CTX_CUDA(ctx, cudaGetLastError());
+        return LZ4B200_OK;
+    }
     // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
     {
         uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
@@ -532,6 +582,13 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
+    if (const char *g = getenv("LZ4B200_THREAD_MIN")) ctx->enc_thread_min = ctx->dec_thread_min = (uint32_t)atoll(g);
+    if (const char *g = getenv("LZ4B200_ENC_THREAD_MIN")) ctx->enc_thread_min = (uint32_t)atoll(g);
+    if (const char *g = getenv("LZ4B200_DEC_THREAD_MIN")) ctx->dec_thread_min = (uint32_t)atoll(g);
+    if (const char *g = getenv("LZ4B200_ENC_THREAD_LANES")) ctx->enc_thread_lanes = atoi(g);
+    if (const char *g = getenv("LZ4B200_DEC_THREAD_LANES")) ctx->dec_thread_lanes = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_THREADS")) ctx->enc_thread_max = std::max(32, atoi(g));
+    if (const char *g = getenv("LZ4B200_DEC_THREADS")) ctx->dec_thread_max = std::max(32, atoi(g));
     if (const char *g = getenv("LZ4B200_DEC_GROUP")) {
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) ctx->dec_group_override = v;
@@ -552,6 +609,7 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
     ctx->d_off_b.release();
     ctx->d_in_len.release(); ctx->d_out_cap.release(); ctx->d_out_len.release(); ctx->d_info.release();
     ctx->d_seg_size.release(); ctx->d_payload_len.release(); ctx->d_status.release();
+    ctx->d_gtab16.release(); ctx->d_ttab16.release();
     delete ctx;
 }
 

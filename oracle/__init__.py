@@ -46,8 +46,8 @@ F_LINKED = 8
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (make -C oracle)."""
-    src = os.path.join(_HERE, "lz4_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("lz4_oracle.c", "lz4_cpu_baseline.c", "lz4_oracle.h", "Makefile")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
 
@@ -89,6 +89,17 @@ def lib():
             f = getattr(L, name)
             f.restype = None
             f.argtypes = [u8p] * 8 + [sz, C.c_int]
+        # performance-oriented CPU baseline + persistent pool (oracle/lz4_cpu_baseline.c)
+        L.lz4cpu_compress_block.restype = i64
+        L.lz4cpu_compress_block.argtypes = [u8p, sz, u8p, sz, C.c_void_p]
+        L.lz4cpu_decompress_block.restype = C.c_int
+        L.lz4cpu_decompress_block.argtypes = [u8p, sz, u8p, sz] + [C.POINTER(sz)] * 3
+        L.lz4cpu_pool_create.restype = C.c_void_p
+        L.lz4cpu_pool_create.argtypes = [C.c_int]
+        L.lz4cpu_pool_destroy.restype = None
+        L.lz4cpu_pool_destroy.argtypes = [C.c_void_p]
+        L.lz4cpu_pool_run.restype = None
+        L.lz4cpu_pool_run.argtypes = [C.c_void_p, C.c_int] + [u8p] * 8 + [sz]
         _lib = L
     return _lib
 
@@ -250,3 +261,57 @@ def compress_batch(src, in_off, in_len, dst, out_off, out_cap, nthreads: int = 1
 
 def decompress_batch(src, in_off, in_len, dst, out_off, out_cap, nthreads: int = 1):
     return _batch(lib().lz4o_decompress_batch, src, in_off, in_len, dst, out_off, out_cap, nthreads)
+
+
+# ---- performance-oriented CPU baseline (oracle/lz4_cpu_baseline.c): same bytes as the functions above ----------
+
+def fast_compress_block(data) -> bytes:
+    a, p, n = _buf(data)
+    out = np.empty(max_output_size(n), dtype=np.uint8)
+    tab = np.empty(4096, dtype=np.uint32)
+    r = lib().lz4cpu_compress_block(p, n, out.ctypes.data, out.size, tab.ctypes.data)
+    assert r >= 0
+    return out[:r].tobytes()
+
+
+def fast_decompress_block(data, cap: int):
+    """(status, bytes, expected, actual) like decompress_block."""
+    a, p, n = _buf(data)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    w, e1, e2 = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+    st = lib().lz4cpu_decompress_block(p, n, out.ctypes.data, cap, C.byref(w), C.byref(e1), C.byref(e2))
+    return st, out[: w.value].tobytes(), e1.value, e2.value
+
+
+class Pool:
+    """Persistent worker threads for the CPU arm of bench.py: threads are created once, every run() hands out the
+    blocks of one batch in chunks from an atomic counter."""
+
+    def __init__(self, nthreads: int):
+        self.nthreads = max(1, int(nthreads))
+        self._h = lib().lz4cpu_pool_create(self.nthreads)
+
+    def _run(self, decode, src, in_off, in_len, dst, out_off, out_cap):
+        nb = len(in_len)
+        out_len = np.zeros(nb, dtype=np.uint32)
+        status = np.zeros(nb, dtype=np.int32)
+        lib().lz4cpu_pool_run(self._h, decode, src.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, dst.ctypes.data,
+                              out_off.ctypes.data, out_cap.ctypes.data, out_len.ctypes.data, status.ctypes.data, nb)
+        return out_len, status
+
+    def compress(self, src, in_off, in_len, dst, out_off, out_cap):
+        return self._run(0, src, in_off, in_len, dst, out_off, out_cap)
+
+    def decompress(self, src, in_off, in_len, dst, out_off, out_cap):
+        return self._run(1, src, in_off, in_len, dst, out_off, out_cap)
+
+    def close(self):
+        if self._h:
+            lib().lz4cpu_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

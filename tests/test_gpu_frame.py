@@ -160,6 +160,44 @@ def test_config4_reduced_epochs(ctx):
     assert frame.decompress_frame(got, ctx) == data.tobytes()
 
 
+def test_config4_fresh_block_at_511(ctx):
+    """The table reposition of FrameEncoder (frame/compress.rs:266-271) on hardware: with 4 MiB blocks the block at
+    absolute index 511 starts a fresh table epoch (FRESH parse), its neighbours continue one (CONT).  Blocks 509..513
+    of the config-4 stream through the device block-range entry point vs the oracle's persistent table driven from
+    the same stream offset."""
+    import torch
+    from lz4_flex_b200 import _native
+    bs, first, nblk = 4 << 20, 509, 5
+    h = np.frombuffer(corpus.load("hdfs.json"), dtype=np.uint8)
+    idx = (np.arange(nblk * bs, dtype=np.int64) + first * bs) % h.size          # config 4: tiled by absolute offset
+    data = h[idx]
+    table = oracle.FrameTable()
+    table.offset = first * bs                                                    # an empty table at this offset == CONT
+    want = b""
+    fresh_seen = []
+    for k in range(nblk):
+        blk = data[k * bs:(k + 1) * bs].tobytes()
+        before = table.offset
+        c = table.compress(blk, bs)
+        fresh_seen.append(table.offset - len(blk) != before)                     # offset was reset before this block
+        assert len(c) < len(blk)
+        want += len(c).to_bytes(4, "little") + c
+    assert fresh_seen == [False, False, True, False, False]
+    assert oracle.compress_block_fresh_h5(data[2 * bs:3 * bs].tobytes()) in want      # block 511 is a FRESH parse
+    L = _native.lib()
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(data).to(dev)
+    bound = L.lz4b200_frame_blocks_bound(d_in.numel(), bs)
+    d_out = torch.zeros(bound, dtype=torch.uint8, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = L.lz4b200_frame_compress_blocks_device(ctx.handle, d_in.data_ptr(), d_in.numel(), bs, first, d_out.data_ptr(),
+                                                bound, d_total.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    torch.cuda.synchronize()
+    got = d_out[: int(d_total.item())].cpu().numpy().tobytes()
+    assert got == want
+
+
 # ---- BlockMode::Linked frames, decode side (SURVEY.md §8 f-3) -----------------------------------------------------------
 
 def _linked_fixtures():

@@ -385,3 +385,53 @@ def test_linked_frame_corruption_is_detected():
     name, f, want = next(_linked_fixtures())                   # has block + content checksums
     bad = bytearray(f); bad[len(f) // 2] ^= 0x55
     assert oracle.frame_decompress(bytes(bad), len(want) + 64)[0] == oracle.FERR_BLOCK_CHECKSUM
+
+
+# ---- the performance-oriented CPU baseline (oracle/lz4_cpu_baseline.c) must be the same function as the oracle ------
+
+def test_fast_baseline_equals_oracle():
+    rng = np.random.default_rng(9)
+    inputs = [corpus.load(f) for f in ("compression_1k.txt", "compression_34k.txt", "compression_65k.txt", "compression_66k_JSON.txt")]
+    inputs += [corpus.load("dickens.txt")[: 1 << 20], corpus.load("hdfs.json")[: 300000], bytes(65536), bytes(70000)]
+    inputs += [corpus.load("compression_66k_JSON.txt")[:n] for n in list(range(0, 40)) + [65534, 65535, 65536]]
+    inputs += [bytes(rng.integers(0, a, n, dtype=np.uint8)) for a in (2, 4, 256) for n in (13, 100, 5000, 66000)]
+    for d in inputs:
+        c = oracle.compress_block(d)
+        assert oracle.fast_compress_block(d) == c, len(d)
+        for cap in (len(d), len(d) + 5, len(d) + 100):
+            assert oracle.fast_decompress_block(c, cap)[:2] == (0, d)
+        if len(d) > 20:
+            assert oracle.fast_decompress_block(c, len(d) - 1) == oracle.decompress_block(c, len(d) - 1)
+    for name, stream, cap, status, out, expected in DECODE_KATS:
+        st_, o, e1, e2 = oracle.fast_decompress_block(bytes(stream), cap)
+        assert (st_, o if status == 0 else b"") == (status, bytes(out) if status == 0 else b"")
+    good = oracle.compress_block(corpus.load("compression_66k_JSON.txt")[:30000])
+    for i in range(2000):
+        if i % 2:
+            b = bytearray(good)
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+            s, cap = bytes(b), 30000
+        else:
+            s, cap = bytes(rng.integers(0, 256, int(rng.integers(1, 120)), dtype=np.uint8)), int(rng.integers(0, 300))
+        a, b_ = oracle.fast_decompress_block(s, cap), oracle.decompress_block(s, cap)
+        assert a[0] == b_[0] and (a[0] != 0 or a[1] == b_[1]) and (a[0] != 2 or a[2:] == b_[2:]), i
+
+
+def test_pool_batches_equal_oracle():
+    nb, B, slot = 300, 65536, 72112
+    data = corpus.tiled("compression_66k_JSON.txt", nb * B)
+    offs = np.arange(nb, dtype=np.uint64) * B
+    lens = np.full(nb, B, dtype=np.uint32)
+    soff = np.arange(nb, dtype=np.uint64) * slot
+    scap = np.full(nb, slot, dtype=np.uint32)
+    c1, c2 = np.zeros(nb * slot, dtype=np.uint8), np.zeros(nb * slot, dtype=np.uint8)
+    l1, s1 = oracle.compress_batch(data, offs, lens, c1, soff, scap, 4)
+    pool = oracle.Pool(5)
+    for _ in range(3):                                        # the pool is reusable
+        l2, s2 = pool.compress(data, offs, lens, c2, soff, scap)
+        assert np.array_equal(l1, l2) and not s2.any()
+        assert all(c1[b * slot: b * slot + int(l1[b])].tobytes() == c2[b * slot: b * slot + int(l1[b])].tobytes() for b in range(nb))
+        back = np.zeros(nb * B, dtype=np.uint8)
+        ol, st = pool.decompress(c2, soff, l2, back, offs, lens)
+        assert not st.any() and (ol == B).all() and np.array_equal(back, data)
+    pool.close()
