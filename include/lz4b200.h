@@ -283,17 +283,33 @@ size_t lz4b200_frame_blocks_bound(size_t in_len, size_t block_size);
 /* Writes the frame header for `info` (7..15 bytes) — FrameInfo::write, header.rs:232-275. */
 size_t lz4b200_frame_write_header(const lz4b200_frame_info *info, uint8_t *out, size_t cap);
 
-/* FrameDecoder::new(r).read_to_end() over all concatenated frames
- *   — src/frame/decompress.rs:109-342.  Host pointers.  *block_status receives the block
- * decoder's code when the result is FRAME_DECOMPRESSION_ERROR.  Frames with linked blocks
- * (frame/decompress.rs:196-222, 277-305; what `lz4`, LZ4F and pyarrow write by default) are decoded
- * too: their blocks form a dependency chain that the device resolves in stream order. */
+/* ONE frame: FrameDecoder::new(r).read_to_end() — src/frame/decompress.rs:109-342, 352-422.  The reference's
+ * reader returns Ok(0) at every EndMark (decompress.rs:310-331; tests/tests.rs:633-647 reads two concatenated frames
+ * with two read_to_end calls), so the unit of this call is the frame that starts at in[0]: it is decoded into `out`,
+ * *consumed receives the input bytes it occupied (header, blocks, EndMark, content checksum) and the caller calls
+ * again with in + *consumed for the next frame.  n == 0, or 4 bytes of magic followed by the end of the input
+ * (decompress.rs:113-128), is a clean end: OK with *written == 0.
+ *   - bytes decoded before a corrupt block / truncation are delivered (*written) together with the error;
+ *   - *block_status receives the block decoder's code for FRAME_DECOMPRESSION_ERROR; *err_expected / *err_actual
+ *     receive ContentLengthError{expected, actual} (frame/mod.rs) or the block's OutputTooSmall{expected, actual};
+ *   - frames with linked blocks (frame/decompress.rs:196-222, 277-305; what `lz4`, LZ4F and pyarrow write by
+ *     default) are decoded too: their blocks form a dependency chain that the device resolves in stream order;
+ *   - device memory is bounded: independent blocks are decoded in groups whose output slots
+ *     (min(block size, 255 x payload) each) fit lz4b200_ctx_set_frame_budget() bytes (default 256 MiB), reusing the
+ *     slots from group to group — the reference decodes any frame in O(block size) memory. */
+lz4b200_status lz4b200_frame_decompress_next(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
+                                             uint8_t *out, size_t cap, size_t *consumed, size_t *written,
+                                             int *block_status, uint64_t *err_expected, uint64_t *err_actual);
+void lz4b200_ctx_set_frame_budget(lz4b200_ctx *ctx, size_t bytes);
+
+/* Convenience: every concatenated frame of `in` through lz4b200_frame_decompress_next, outputs back to back
+ * (stops at the first error; frame boundaries are not reported — use _next when they matter). */
 lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, size_t n,
                                         uint8_t *out, size_t cap, size_t *written,
                                         int *block_status);
 
-/* Total decoded size of all frames in `in` when every frame carries content_size; otherwise
- * an upper bound (#blocks x max block size).  Host-side header walk only. */
+/* Upper bound of the decoded size of all frames in `in`: per block min(frame block size, 255 x payload) (stored
+ * blocks: their length).  The header's content_size is deliberately ignored (untrusted).  Host-side walk only. */
 lz4b200_status lz4b200_frame_decoded_bound(const uint8_t *in, size_t n, size_t *bound);
 
 /* XXH32 (twox-hash XxHash32, Cargo.toml:51) — used for header/block/content checksums.

@@ -115,6 +115,9 @@ SIGNATURES = {
     "lz4b200_frame_write_header": (_sz, [C.POINTER(FrameInfoC), _vp, _sz]),
     "lz4b200_frame_decompress": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(C.c_int)]),
     "lz4b200_frame_decoded_bound": (_i32, [_vp, _sz, _psz]),
+    "lz4b200_frame_decompress_next": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz, _psz, C.POINTER(C.c_int),
+                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "lz4b200_ctx_set_frame_budget": (None, [_vp, _sz]),
     "lz4b200_xxh32": (_u32, [_vp, _sz, _u32]),
     "lz4b200_xxh32_reset": (None, [_vp, _u32]),
     "lz4b200_xxh32_update": (None, [_vp, _vp, _sz]),

@@ -15,6 +15,7 @@
 
 #include "lz4b200_kernels.cuh"
 #include "lz4b200_thread_kernels.cuh"
+#include "lz4b200_solo_kernel.cuh"
 
 using namespace lz4b200;
 
@@ -274,7 +275,12 @@ struct lz4b200_ctx {
     uint32_t enc_thread_min = 4096, dec_thread_min = 4096;
     int enc_thread_lanes = 0, dec_thread_lanes = 0;   // 0: chosen from the batch size
     uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
+    // K1-S (one chain per CTA in shared memory, lz4b200_solo_kernel.cuh): every batch of blocks > 64 KiB, and small
+    // batches of small blocks (fewer chains than the GPU has half-SMs).  LZ4B200_ENC_SOLO=0 disables it (A/B aid).
+    int enc_solo = 1, enc_solo_ctas_per_sm = 0;
+    uint32_t enc_solo_small_max = 0;          // set from the SM count at context creation
     std::string last_error;
+    size_t frame_budget = 256u << 20;         // device bytes the frame decoder's block slots / staged input may take per group
 
     // scratch for host-pointer and frame entry points
     DevBuf<uint8_t> d_in, d_out, d_slots, d_flags, d_pick, d_dict;
@@ -387,6 +393,12 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     if (!tickets) tickets = ctx->d_tickets;
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
+    if (!a.dict_len && ctx->enc_solo && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
+        const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm));
+        lz4_compress_blocks_solo<<<grid, 64, kSoloSmemBytes, s>>>(a, tickets + 4);
+        CTX_CUDA(ctx, cudaGetLastError());
+        return LZ4B200_OK;
+    }
     if (!a.dict_len && max_in_len != 0 && max_in_len <= 65536u && a.nblocks >= ctx->enc_thread_min) {
         // K1-T: one block per thread, 8 KiB table per thread in global memory (one region per concurrent launch)
         const uint32_t threads = std::min(a.nblocks, ctx->enc_thread_max);
@@ -556,6 +568,14 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
                             &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>, kEnc32Pairs * 64,
                             split_smem_bytes<uint32_t, kEnc32Pairs>()), "occupancy enc32 split");
     }
+    if (ok) {
+        ok = ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kSoloSmemBytes), "solo smem") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo_ctas_per_sm, lz4_compress_blocks_solo, 64,
+                                                                      kSoloSmemBytes), "occupancy solo");
+        if (ctx->enc_solo_ctas_per_sm < 1) ctx->enc_solo = 0;
+        ctx->enc_solo_small_max = (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm);
+    }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
         fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
         lz4b200_ctx_destroy(ctx);
@@ -582,6 +602,8 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_THREAD_MIN")) ctx->enc_thread_min = ctx->dec_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_ENC_THREAD_MIN")) ctx->enc_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_DEC_THREAD_MIN")) ctx->dec_thread_min = (uint32_t)atoll(g);
@@ -1434,6 +1456,13 @@ struct FrameRef {
 
 }  // namespace
 
+// Upper bound of what one block can decode to: its frame's block size, and never more than 255 output bytes per
+// input byte (a length-extension byte of 0xFF stands for 255 bytes; nothing in the format is denser).
+static inline uint64_t block_decoded_cap(uint64_t payload_len, uint64_t bs)
+{
+    return std::min<uint64_t>(bs, payload_len * 255ull + 16ull);
+}
+
 lz4b200_status lz4b200_frame_decoded_bound(const uint8_t *in, size_t n, size_t *bound)
 {
     if (!bound || (!in && n)) return LZ4B200_INVALID_ARGUMENT;
@@ -1441,7 +1470,6 @@ lz4b200_status lz4b200_frame_decoded_bound(const uint8_t *in, size_t n, size_t *
     while (ip + 4 <= n) {
         uint32_t magic = rd32(in + ip);
         size_t bs; unsigned flg = 0x20;
-        bool sized = false; uint64_t csize = 0;
         if (magic == 0x184C2102u) { ip += 4; bs = 8u << 20; }
         else {
             if (n - ip < 7 || magic != 0x184D2204u) break;
@@ -1451,203 +1479,252 @@ lz4b200_status lz4b200_frame_decoded_bound(const uint8_t *in, size_t n, size_t *
             if (!bs) break;
             size_t need = 7 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0);
             if (n - ip < need) break;
-            if (flg & 8) { memcpy(&csize, in + ip + 6, 8); sized = true; }
             ip += need;
         }
-        size_t frame_total = 0;
+        // The header's content_size is NOT used: it is untrusted, and a frame whose real size differs must still be
+        // delivered in full before ContentLengthError is reported (frame/decompress.rs:312-321).
         for (;;) {
             if (n - ip < 4) { ip = n; break; }
             uint32_t word = rd32(in + ip); ip += 4;
             if (word == 0) { if (flg & 4) ip += 4; break; }
             size_t len = word & 0x7fffffffu;
-            frame_total += (word & 0x80000000u) ? len : bs;
+            total += (word & 0x80000000u) ? len : (size_t)block_decoded_cap(len, bs);
             ip += len + ((flg & 0x10) ? 4 : 0);
             if (ip > n) { ip = n; break; }
         }
-        total += sized ? std::min<uint64_t>(csize, frame_total) : frame_total;
     }
     *bound = total;
     return LZ4B200_OK;
 }
 
+void lz4b200_ctx_set_frame_budget(lz4b200_ctx *ctx, size_t bytes)
+{
+    if (ctx) ctx->frame_budget = std::max<size_t>(bytes, 1u << 20);
+}
+
+// One frame.  Host walk of its header and BlockInfo chain (frame/decompress.rs:109-342), then the blocks are decoded
+// in groups whose device slots fit the context's frame budget (slots are reused from group to group), so a frame of
+// many short blocks costs O(budget) device memory, not #blocks x block size.
+lz4b200_status lz4b200_frame_decompress_next(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
+                                             size_t *consumed, size_t *written, int *block_status,
+                                             uint64_t *err_expected, uint64_t *err_actual)
+{
+    if (!ctx || !written || !consumed || (!in && n) || (!out && cap)) return LZ4B200_INVALID_ARGUMENT;
+    *written = 0; *consumed = 0;
+    if (block_status) *block_status = 0;
+    if (err_expected) *err_expected = 0;
+    if (err_actual) *err_actual = 0;
+    if (n == 0) return LZ4B200_OK;                          // read_frame_info: 0 bytes where a frame would start = end of data
+
+    // ---- header -----------------------------------------------------------------------------------
+    std::vector<FrameBlockRef> blocks;
+    lz4b200_status walk_err = LZ4B200_OK;
+    size_t ip = 0;
+    size_t bs; unsigned flg = 0x20;
+    FrameRef fr{0, 0, false, false, false, 0, 0};
+    if (n < 4) { *consumed = n; return LZ4B200_FRAME_IO_EOF; }
+    const uint32_t magic = rd32(in);
+    if (magic == 0x184C2102u) {                             // legacy frame: header.rs:285-291
+        ip = 4; bs = 8u << 20;
+    } else {
+        if (n == 4) { *consumed = 4; return LZ4B200_OK; }   // decompress.rs:124-128: nothing after the magic = end of data
+        if (n < 7) { *consumed = n; return LZ4B200_FRAME_IO_EOF; }
+        if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) return LZ4B200_FRAME_SKIPPABLE;
+        if (magic != 0x184D2204u) return LZ4B200_FRAME_WRONG_MAGIC;
+        flg = in[4];
+        const uint8_t bd = in[5];
+        const size_t need = 7 + ((flg & 0x08) ? 8 : 0) + ((flg & 0x01) ? 4 : 0);
+        if (n < need) { *consumed = n; return LZ4B200_FRAME_IO_EOF; }
+        if ((flg & 0xC0) != 0x40) return LZ4B200_FRAME_UNSUPPORTED_VERSION;
+        if ((flg & 0x02) || (bd & 0x8F)) return LZ4B200_FRAME_RESERVED_BITS;
+        const int id = (bd >> 4) & 7;
+        if (id < 4) return LZ4B200_FRAME_UNSUPPORTED_BLOCKSIZE;
+        bs = block_size_bytes(id);
+        size_t o = 6;
+        if (flg & 0x08) { memcpy(&fr.content_size, in + o, 8); fr.has_size = true; o += 8; }
+        if (flg & 0x01) o += 4;
+        if ((uint8_t)(lz4b200_xxh32(in + 4, o - 4, 0) >> 8) != in[o]) return LZ4B200_FRAME_HEADER_CHECKSUM;
+        if (flg & 0x01) return LZ4B200_FRAME_DICTIONARY;
+        fr.linked = !(flg & 0x20);
+        ip = o + 1;
+    }
+    // ---- BlockInfo chain --------------------------------------------------------------------------
+    for (;;) {
+        if (n - ip < 4) { ip = n; break; }                  // EOF where a BlockInfo is due: decompress.rs:236-243
+        const uint32_t word = rd32(in + ip); ip += 4;
+        if (word == 0) {                                     // EndMark
+            fr.closed = true;
+            if (flg & 0x04) {
+                if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; ip = n; break; }
+                fr.has_checksum = true; fr.content_checksum = rd32(in + ip); ip += 4;
+            }
+            break;
+        }
+        const size_t len = word & 0x7fffffffu;
+        if (len > bs) { walk_err = LZ4B200_FRAME_BLOCK_TOO_BIG; break; }
+        if (n - ip < len) { walk_err = LZ4B200_FRAME_IO_EOF; ip = n; break; }
+        const size_t payload = ip; ip += len;
+        if (flg & 0x10) {
+            if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; ip = n; break; }
+            if (rd32(in + ip) != lz4b200_xxh32(in + payload, len, 0)) { walk_err = LZ4B200_FRAME_BLOCK_CHECKSUM; break; }
+            ip += 4;
+        }
+        blocks.push_back({payload, (uint32_t)len, (uint32_t)bs, (word & 0x80000000u) != 0, 0});
+        fr.nblocks++;
+    }
+    *consumed = ip;
+
+    // ---- decode every block seen before the walk stopped, group by group ---------------------------
+    const uint32_t nb = (uint32_t)blocks.size();
+    uint64_t total = 0;
+    Xxh32 content(0);
+    if (nb) {
+        DeviceGuard guard(ctx->device);
+        cudaStream_t s = ctx->stream;
+        const bool linked = fr.linked && nb > 1;
+        std::vector<uint64_t> h_in_off, h_slot_off, seg, h_soff;
+        std::vector<uint32_t> h_in_len, h_cap, produced, h_first, h_slen;
+        std::vector<uint8_t> h_pick;
+        std::vector<int32_t> status;
+        std::vector<uint64_t> expected;
+        for (uint32_t g0 = 0; g0 < nb;) {
+            // a group: as many blocks as fit the budget (a linked frame is one dependency chain: one group)
+            uint32_t g1 = g0;
+            uint64_t slot_total = 0;
+            while (g1 < nb) {
+                const uint64_t c = blocks[g1].stored ? 0 : block_decoded_cap(blocks[g1].payload_len, bs);
+                const uint64_t in_span = blocks[g1].payload_off + blocks[g1].payload_len - blocks[g0].payload_off;
+                if (!linked && g1 > g0 && (slot_total + c > ctx->frame_budget || in_span > ctx->frame_budget)) break;
+                slot_total += (c + 15) & ~15ull;
+                g1++;
+            }
+            const uint32_t gn = g1 - g0;
+            const uint64_t in_lo = blocks[g0].payload_off;
+            const uint64_t in_bytes = blocks[g1 - 1].payload_off + blocks[g1 - 1].payload_len - in_lo;
+            h_in_off.assign(gn, 0); h_slot_off.assign(gn, 0); h_in_len.assign(gn, 0); h_cap.assign(gn, 0);
+            h_pick.assign(gn, 0); produced.assign(gn, 0); status.assign(gn, 0); expected.assign(gn, 0); seg.assign(gn + 1, 0);
+            uint64_t so = 0;
+            for (uint32_t k = 0; k < gn; k++) {
+                const FrameBlockRef &b = blocks[g0 + k];
+                h_in_off[k] = b.payload_off - in_lo;
+                h_in_len[k] = b.stored ? 0 : b.payload_len;            // stored blocks are only gathered
+                h_pick[k] = b.stored ? 1 : 0;
+                h_slot_off[k] = so;
+                h_cap[k] = b.stored ? 0 : (uint32_t)block_decoded_cap(b.payload_len, bs);
+                so += ((uint64_t)h_cap[k] + 15) & ~15ull;
+            }
+            CTX_CUDA(ctx, ctx->d_in.reserve(in_bytes + 16));
+            CTX_CUDA(ctx, ctx->d_slots.reserve(so + 16));
+            CTX_CUDA(ctx, ctx->d_in_off.reserve(gn)); CTX_CUDA(ctx, ctx->d_in_len.reserve(gn));
+            CTX_CUDA(ctx, ctx->d_out_off.reserve(gn)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(gn));
+            CTX_CUDA(ctx, ctx->d_out_len.reserve(gn)); CTX_CUDA(ctx, ctx->d_status.reserve(gn));
+            CTX_CUDA(ctx, ctx->d_expected.reserve(gn));
+            CTX_CUDA(ctx, ctx->d_pick.reserve(gn)); CTX_CUDA(ctx, ctx->d_seg_off.reserve(gn + 1));
+            CTX_CUDA(ctx, ctx->d_payload_len.reserve(gn));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in + in_lo, in_bytes, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), gn * 8, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, h_in_len.data(), gn * 4, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), gn * 8, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), gn * 4, cudaMemcpyHostToDevice, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pick.p, h_pick.data(), gn, cudaMemcpyHostToDevice, s));
+            BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_slots.p, ctx->d_out_off.p,
+                        ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, ctx->d_expected.p, gn, nullptr};
+            lz4b200_status st;
+            if (linked) {
+                // BlockMode::Linked (frame/decompress.rs:196-222): the blocks of a frame form a dependency chain; the
+                // linked kernel resolves offsets that reach before a block in the outputs of its predecessors
+                h_first.assign(gn, 0); h_slen.assign(gn, 0); h_soff.assign(gn, 0);
+                for (uint32_t k = 0; k < gn; k++) {
+                    h_slen[k] = blocks[g0 + k].stored ? blocks[g0 + k].payload_len : 0;
+                    h_soff[k] = h_in_off[k];
+                }
+                CTX_CUDA(ctx, ctx->d_link_first.reserve(gn)); CTX_CUDA(ctx, ctx->d_stored_len.reserve(gn));
+                CTX_CUDA(ctx, ctx->d_stored_off.reserve(gn)); CTX_CUDA(ctx, ctx->d_done.reserve(gn));
+                CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_link_first.p, h_first.data(), gn * 4, cudaMemcpyHostToDevice, s));
+                CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_len.p, h_slen.data(), gn * 4, cudaMemcpyHostToDevice, s));
+                CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_off.p, h_soff.data(), gn * 8, cudaMemcpyHostToDevice, s));
+                CTX_CUDA(ctx, cudaMemsetAsync(ctx->d_done.p, 0, gn * 4, s));
+                a.link_first = ctx->d_link_first.p; a.stored_off = ctx->d_stored_off.p;
+                a.stored_len = ctx->d_stored_len.p; a.done = ctx->d_done.p;
+                a.tickets = ctx->d_tickets;
+                const uint32_t grid = std::min<uint32_t>((gn + 3) / 4, (uint32_t)ctx->sm_count * 8);
+                lz4_decompress_blocks_linked<32><<<grid, 128, 0, s>>>(a);
+                st = ctx->check(cudaGetLastError(), "linked decode launch") ? LZ4B200_OK : LZ4B200_CUDA_ERROR;
+            } else {
+                st = launch_decompress(ctx, a, s);
+            }
+            if (st != LZ4B200_OK) return st;
+            CTX_CUDA(ctx, cudaMemcpyAsync(produced.data(), ctx->d_out_len.p, gn * 4, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status.p, gn * 4, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaMemcpyAsync(expected.data(), ctx->d_expected.p, gn * 8, cudaMemcpyDeviceToHost, s));
+            CTX_CUDA(ctx, cudaStreamSynchronize(s));
+
+            // first failing block (stream order) wins over anything the walk found later
+            uint32_t good = gn;
+            for (uint32_t k = 0; k < gn; k++) {
+                if (blocks[g0 + k].stored) { produced[k] = blocks[g0 + k].payload_len; status[k] = 0; continue; }
+                if (status[k] != 0) { good = k; break; }
+            }
+            uint64_t gtotal = 0;
+            for (uint32_t k = 0; k < good; k++) { seg[k] = gtotal; gtotal += produced[k]; }
+            seg[good] = gtotal;
+            if (total + gtotal > cap) { *written = total; return LZ4B200_FRAME_OUTPUT_FULL; }
+            if (gtotal) {
+                CTX_CUDA(ctx, ctx->d_out.reserve(gtotal + 16));
+                CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_seg_off.p, seg.data(), (good + 1) * 8, cudaMemcpyHostToDevice, s));
+                CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_payload_len.p, produced.data(), good * 4, cudaMemcpyHostToDevice, s));
+                GatherArgs g{ctx->d_slots.p, ctx->d_in.p, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p,
+                             ctx->d_payload_len.p, ctx->d_pick.p, nullptr, ctx->d_out.p, ctx->d_seg_off.p, good};
+                gather_segments_kernel<<<std::min<uint32_t>(good, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+                CTX_CUDA(ctx, cudaGetLastError());
+                CTX_CUDA(ctx, cudaMemcpyAsync(out + total, ctx->d_out.p, gtotal, cudaMemcpyDeviceToHost, s));
+                CTX_CUDA(ctx, cudaStreamSynchronize(s));
+                if (fr.has_checksum) content.update(out + total, gtotal);
+            }
+            total += gtotal;
+            *written = total;
+            if (good < gn) {
+                if (block_status) *block_status = status[good];
+                if (status[good] == LZ4B200_DEC_OUTPUT_TOO_SMALL) {
+                    if (err_expected) *err_expected = expected[good];
+                    if (err_actual) *err_actual = h_cap[good];
+                }
+                return LZ4B200_FRAME_DECOMPRESSION_ERROR;
+            }
+            g0 = g1;
+        }
+    }
+    if (walk_err != LZ4B200_OK) return walk_err;
+
+    // ---- content size / checksum at the EndMark (decompress.rs:312-331) -----------------------------
+    if (fr.closed) {
+        if (fr.has_size && total != fr.content_size) {
+            if (err_expected) *err_expected = fr.content_size;
+            if (err_actual) *err_actual = total;
+            return LZ4B200_FRAME_CONTENT_LENGTH;
+        }
+        if (fr.has_checksum && content.digest() != fr.content_checksum) return LZ4B200_FRAME_CONTENT_CHECKSUM;
+    }
+    return LZ4B200_OK;
+}
+
+// Every concatenated frame of `in`, back to back (a convenience over lz4b200_frame_decompress_next: the reference's
+// reader stops at each EndMark, frame/decompress.rs:310-331, and a caller that cares about frame boundaries uses _next).
 lz4b200_status lz4b200_frame_decompress(lz4b200_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap,
                                         size_t *written, int *block_status)
 {
     if (!ctx || !written || (!in && n) || (!out && cap)) return LZ4B200_INVALID_ARGUMENT;
     *written = 0;
     if (block_status) *block_status = 0;
-
-    // ---- host walk: frame headers and BlockInfo chain (frame/decompress.rs:109-342) ----------
-    std::vector<FrameBlockRef> blocks;
-    std::vector<FrameRef> frames;
-    lz4b200_status walk_err = LZ4B200_OK;
     size_t ip = 0;
-    while (ip < n && walk_err == LZ4B200_OK) {
-        if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-        uint32_t magic = rd32(in + ip);
-        size_t bs; unsigned flg = 0x20;
-        FrameRef fr{(uint32_t)blocks.size(), 0, false, false, false, 0, 0};
-        if (magic == 0x184C2102u) {                         // legacy frame: header.rs:285-291
-            ip += 4; bs = 8u << 20;
-        } else {
-            if (n - ip < 7) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-            if (magic >= 0x184D2A50u && magic <= 0x184D2A5Fu) { walk_err = LZ4B200_FRAME_SKIPPABLE; break; }
-            if (magic != 0x184D2204u) { walk_err = LZ4B200_FRAME_WRONG_MAGIC; break; }
-            const size_t h = ip + 4;
-            flg = in[h];
-            const uint8_t bd = in[h + 1];
-            const size_t need = 7 + ((flg & 0x08) ? 8 : 0) + ((flg & 0x01) ? 4 : 0);
-            if (n - ip < need) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-            if ((flg & 0xC0) != 0x40) { walk_err = LZ4B200_FRAME_UNSUPPORTED_VERSION; break; }
-            if ((flg & 0x02) || (bd & 0x8F)) { walk_err = LZ4B200_FRAME_RESERVED_BITS; break; }
-            const int id = (bd >> 4) & 7;
-            if (id < 4) { walk_err = LZ4B200_FRAME_UNSUPPORTED_BLOCKSIZE; break; }
-            bs = block_size_bytes(id);
-            size_t o = h + 2;
-            if (flg & 0x08) { memcpy(&fr.content_size, in + o, 8); fr.has_size = true; o += 8; }
-            if (flg & 0x01) o += 4;
-            if ((uint8_t)(lz4b200_xxh32(in + h, o - h, 0) >> 8) != in[o]) { walk_err = LZ4B200_FRAME_HEADER_CHECKSUM; break; }
-            if (flg & 0x01) { walk_err = LZ4B200_FRAME_DICTIONARY; break; }
-            fr.linked = !(flg & 0x20);
-            ip = o + 1;
-        }
-        const uint32_t fidx = (uint32_t)frames.size();
-        for (;;) {
-            if (n - ip < 4) { ip = n; break; }              // EOF where a BlockInfo is due: decompress.rs:236-243
-            const uint32_t word = rd32(in + ip); ip += 4;
-            if (word == 0) {                                 // EndMark
-                fr.closed = true;
-                if (flg & 0x04) {
-                    if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-                    fr.has_checksum = true; fr.content_checksum = rd32(in + ip); ip += 4;
-                }
-                break;
-            }
-            const size_t len = word & 0x7fffffffu;
-            if (len > bs) { walk_err = LZ4B200_FRAME_BLOCK_TOO_BIG; break; }
-            if (n - ip < len) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-            const size_t payload = ip; ip += len;
-            if (flg & 0x10) {
-                if (n - ip < 4) { walk_err = LZ4B200_FRAME_IO_EOF; break; }
-                if (rd32(in + ip) != lz4b200_xxh32(in + payload, len, 0)) { walk_err = LZ4B200_FRAME_BLOCK_CHECKSUM; break; }
-                ip += 4;
-            }
-            blocks.push_back({payload, (uint32_t)len, (uint32_t)bs, (word & 0x80000000u) != 0, fidx});
-            fr.nblocks++;
-        }
-        frames.push_back(fr);
-    }
-
-    // ---- decode every block seen before the walk stopped ---------------------------------------
-    const uint32_t nb = (uint32_t)blocks.size();
-    std::vector<uint32_t> produced(nb, 0);
-    std::vector<int32_t> status(nb, 0);
-    std::vector<uint64_t> seg(nb + 1, 0);
-    if (nb) {
-        DeviceGuard guard(ctx->device);
-        cudaStream_t s = ctx->stream;
-        std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
-        std::vector<uint32_t> h_in_len(nb), h_cap(nb);
-        std::vector<uint8_t> h_pick(nb);
-        uint64_t slot_total = 0;
-        for (uint32_t b = 0; b < nb; b++) {
-            h_in_off[b] = blocks[b].payload_off;
-            h_in_len[b] = blocks[b].stored ? 0 : blocks[b].payload_len;   // stored blocks are only gathered
-            h_pick[b] = blocks[b].stored ? 1 : 0;
-            h_slot_off[b] = slot_total;
-            h_cap[b] = blocks[b].stored ? 0 : blocks[b].max_out;
-            slot_total += h_cap[b];
-        }
-        CTX_CUDA(ctx, ctx->d_in.reserve(n + 16));
-        CTX_CUDA(ctx, ctx->d_slots.reserve(slot_total + 16));
-        CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));
-        CTX_CUDA(ctx, ctx->d_out_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_out_cap.reserve(nb));
-        CTX_CUDA(ctx, ctx->d_out_len.reserve(nb)); CTX_CUDA(ctx, ctx->d_status.reserve(nb));
-        CTX_CUDA(ctx, ctx->d_pick.reserve(nb)); CTX_CUDA(ctx, ctx->d_seg_off.reserve(nb + 1));
-        CTX_CUDA(ctx, ctx->d_payload_len.reserve(nb));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in.p, in, n, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_off.p, h_in_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_len.p, h_in_len.data(), nb * 4, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_off.p, h_slot_off.data(), nb * 8, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_out_cap.p, h_cap.data(), nb * 4, cudaMemcpyHostToDevice, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pick.p, h_pick.data(), nb, cudaMemcpyHostToDevice, s));
-        BatchArgs a{ctx->d_in.p, ctx->d_in_off.p, ctx->d_in_len.p, nullptr, ctx->d_slots.p, ctx->d_out_off.p,
-                    ctx->d_out_cap.p, ctx->d_out_len.p, ctx->d_status.p, nullptr, nb, nullptr};
-        bool any_linked = false;
-        for (const FrameRef &fr : frames) any_linked |= fr.linked && fr.nblocks > 1;
-        lz4b200_status st;
-        if (any_linked) {
-            // BlockMode::Linked (frame/decompress.rs:196-222): the blocks of a frame form a dependency chain; the
-            // linked kernel resolves offsets that reach before a block in the outputs of its predecessors
-            std::vector<uint32_t> h_first(nb), h_slen(nb);
-            std::vector<uint64_t> h_soff(nb);
-            for (uint32_t b = 0; b < nb; b++) {
-                const FrameRef &fr = frames[blocks[b].frame_idx];
-                h_first[b] = fr.linked ? fr.first_block : b;
-                h_slen[b] = blocks[b].stored ? blocks[b].payload_len : 0;
-                h_soff[b] = blocks[b].payload_off;
-                // a stored block of zero length would read as "compressed": give it no work and no history instead
-                if (blocks[b].stored && blocks[b].payload_len == 0) { h_slen[b] = 0; h_in_len[b] = 0; }
-            }
-            CTX_CUDA(ctx, ctx->d_link_first.reserve(nb)); CTX_CUDA(ctx, ctx->d_stored_len.reserve(nb));
-            CTX_CUDA(ctx, ctx->d_stored_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_done.reserve(nb));
-            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_link_first.p, h_first.data(), nb * 4, cudaMemcpyHostToDevice, s));
-            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_len.p, h_slen.data(), nb * 4, cudaMemcpyHostToDevice, s));
-            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_stored_off.p, h_soff.data(), nb * 8, cudaMemcpyHostToDevice, s));
-            CTX_CUDA(ctx, cudaMemsetAsync(ctx->d_done.p, 0, nb * 4, s));
-            CTX_CUDA(ctx, cudaStreamSynchronize(s));         // h_first & co. are locals
-            a.link_first = ctx->d_link_first.p; a.stored_off = ctx->d_stored_off.p;
-            a.stored_len = ctx->d_stored_len.p; a.done = ctx->d_done.p;
-            a.tickets = ctx->d_tickets;
-            const uint32_t grid = std::min<uint32_t>((nb + 3) / 4, (uint32_t)ctx->sm_count * 8);
-            lz4_decompress_blocks_linked<32><<<grid, 128, 0, s>>>(a);
-            st = ctx->check(cudaGetLastError(), "linked decode launch") ? LZ4B200_OK : LZ4B200_CUDA_ERROR;
-        } else {
-            st = launch_decompress(ctx, a, s);
-        }
+    while (ip < n) {
+        size_t used = 0, w = 0;
+        const lz4b200_status st = lz4b200_frame_decompress_next(ctx, in + ip, n - ip, out + *written, cap - *written, &used,
+                                                                &w, block_status, nullptr, nullptr);
+        *written += w;
         if (st != LZ4B200_OK) return st;
-        CTX_CUDA(ctx, cudaMemcpyAsync(produced.data(), ctx->d_out_len.p, nb * 4, cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(ctx, cudaMemcpyAsync(status.data(), ctx->d_status.p, nb * 4, cudaMemcpyDeviceToHost, s));
-        CTX_CUDA(ctx, cudaStreamSynchronize(s));
-
-        // first failing block (stream order) wins over anything the walk found later
-        uint32_t good = nb;
-        for (uint32_t b = 0; b < nb; b++) {
-            if (blocks[b].stored) { produced[b] = blocks[b].payload_len; status[b] = 0; continue; }
-            if (status[b] != 0) { good = b; break; }
-        }
-        uint64_t total = 0;
-        for (uint32_t b = 0; b < good; b++) { seg[b] = total; total += produced[b]; }
-        seg[good] = total;
-        const bool overflow = total > cap;
-        if (!overflow && good) {
-            CTX_CUDA(ctx, ctx->d_out.reserve(total + 16));
-            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_seg_off.p, seg.data(), (good + 1) * 8, cudaMemcpyHostToDevice, s));
-            CTX_CUDA(ctx, cudaMemcpyAsync(ctx->d_payload_len.p, produced.data(), good * 4, cudaMemcpyHostToDevice, s));
-            GatherArgs g{ctx->d_slots.p, ctx->d_in.p, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p,
-                         ctx->d_payload_len.p, ctx->d_pick.p, nullptr, ctx->d_out.p, ctx->d_seg_off.p, good};
-            gather_segments_kernel<<<std::min<uint32_t>(good, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
-            CTX_CUDA(ctx, cudaGetLastError());
-            CTX_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out.p, total, cudaMemcpyDeviceToHost, s));
-            CTX_CUDA(ctx, cudaStreamSynchronize(s));
-        }
-        if (overflow) return LZ4B200_FRAME_OUTPUT_FULL;
-        *written = total;
-        if (good < nb) {
-            if (block_status) *block_status = status[good];
-            return LZ4B200_FRAME_DECOMPRESSION_ERROR;
-        }
-    }
-    if (walk_err != LZ4B200_OK) return walk_err;
-
-    // ---- per-frame content size / checksum (decompress.rs:312-331) -----------------------------
-    for (const FrameRef &fr : frames) {
-        if (!fr.closed) continue;
-        uint64_t begin = fr.nblocks ? seg[fr.first_block] : 0, len = 0;
-        for (uint32_t b = fr.first_block; b < fr.first_block + fr.nblocks; b++) len += produced[b];
-        if (fr.has_size && len != fr.content_size) return LZ4B200_FRAME_CONTENT_LENGTH;
-        if (fr.has_checksum && lz4b200_xxh32(out + begin, len, 0) != fr.content_checksum)
-            return LZ4B200_FRAME_CONTENT_CHECKSUM;
+        if (used == 0) break;
+        ip += used;
     }
     return LZ4B200_OK;
 }

@@ -141,22 +141,20 @@ struct Appender {
 };
 
 // =============================================================================================
-// K1-T: compress_internal (compress.rs:318-489) for one block, one thread.
-//   tab: 4096 entries owned by this thread, already filled with 0 (FRESH: position 0 is a legal candidate,
-//        compress.rs:353-359) or with TabT's all-ones value (CONT: entries of earlier blocks never match,
-//        compress.rs:403-429).  Entries hold block-relative positions.
-// Returns the compressed size.  The caller has checked cap >= get_maximum_output_size(n) (compress.rs:338-340).
+// The parse of compress_internal (compress.rs:318-489) for one block, run by ONE thread, as a template over
+//   InA/B: byte-stream views of the input (rd8(pos), byte(pos)): cursor side and candidate side
+//   Sink : receives every finished sequence as (anchor, match start, offset, match end) and the final literal run
+//   tab  : 4096 entries owned by this thread, already filled with 0 (FRESH: position 0 is a legal candidate,
+//          compress.rs:353-359) or with TabT's all-ones value (CONT: entries of earlier blocks never match,
+//          compress.rs:403-429).  Entries hold block-relative positions.
+// One loop, two states: a probe (compress.rs:373-439) or 8 bytes of forward extension (:156-216) per iteration,
+// so lanes of a warp that are in different phases of their blocks do not wait for each other's loop trip counts.
 // =============================================================================================
-template <typename TabT>
-TC_FN uint32_t encode_block_thread(const uint8_t *src, uint32_t n, uint8_t *dst, TabT *tab, bool cont, bool h5)
+template <typename TabT, typename InA, typename InB, typename Sink>
+TC_FN void parse_block_thread(InA &in, InB &cs, uint32_t n, TabT *tab, bool cont, bool h5, Sink &sink)
 {
     constexpr uint32_t kInvalid = (uint32_t)(TabT)~(TabT)0;
-    Stream<true> in, cs;                       // cursor side / candidate side (cs also serves the literal copies)
-    in.init(src, n); cs.init(src, n);
-    Appender out;
-    out.init(dst);
     uint32_t anchor = 0;
-
     if (n >= 13u) {                            // compress.rs:343-346: shorter inputs are one literal run
         const uint32_t last_probe = n - 12u, lim = n - 6u;
         uint32_t cur = 0, nm = 32u;
@@ -193,52 +191,71 @@ TC_FN uint32_t encode_block_thread(const uint8_t *src, uint32_t n, uint8_t *dst,
                 ecur += k;
                 if (k == 8u && ecur < lim) continue;
             }
-            // ---- the sequence is complete: re-insert (compress.rs:460-461) and emit (:463-486)
+            // ---- the sequence is complete: re-insert (compress.rs:460-461) and hand over (:463-486)
             const uint32_t end = ecur;
             {
                 const uint64_t v2 = in.rd8(end - 2u);
                 tab[h5 ? slot5(v2) : slot4(v2)] = (TabT)(end - 2u);
             }
-            const uint32_t lit = mpos - anchor, extra = end - mpos - 4u;
-            const uint32_t tok = ((lit < 15u ? lit : 15u) << 4) | (extra < 15u ? extra : 15u);
-            if (lit == 0u && extra < 15u + 255u) {         // token + offset (+ one length byte) in one go
-                uint64_t v = tok | ((uint64_t)dist << 8);
-                uint32_t k = 3u;
-                if (extra >= 15u) { v |= (uint64_t)(extra - 15u) << 24; k = 4u; }
-                out.put(v, k);
-            } else {
-                out.put(tok, 1u);
-                if (lit >= 15u) {                          // write_integer: compress.rs:224-233
-                    uint32_t r = lit - 15u;
-                    for (; r >= 255u; r -= 255u) out.put(0xffu, 1u);
-                    out.put(r, 1u);
-                }
-                for (uint32_t i = 0; i < lit; i += 8u) out.put(cs.rd8(anchor + i), lit - i < 8u ? lit - i : 8u);
-                out.put(dist, 2u);
-                if (extra >= 15u) {
-                    uint32_t r = extra - 15u;
-                    for (; r >= 255u; r -= 255u) out.put(0xffu, 1u);
-                    out.put(r, 1u);
-                }
-            }
+            sink.sequence(anchor, mpos, dist, end);
             anchor = cur = end;
             nm = 32u;
             ext = false;
         }
     }
-    // handle_last_literals: compress.rs:237-247
+    sink.tail(anchor, n);                      // handle_last_literals: compress.rs:237-247
+}
+
+// Sink that writes the LZ4 byte stream directly (K1-T): token / length bytes / literals / offset (compress.rs:463-486)
+// through a write-combining Appender; literals are read through the candidate-side stream, which is idle then.
+template <typename In>
+struct DirectSink {
+    Appender out;
+    In *lits;
+    TC_MFN void put_len(uint32_t r)                        // write_integer: compress.rs:224-233
+    {
+        for (; r >= 255u; r -= 255u) out.put(0xffu, 1u);
+        out.put(r, 1u);
+    }
+    TC_MFN void sequence(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end)
+    {
+        const uint32_t lit = mpos - anchor, extra = end - mpos - 4u;
+        const uint32_t tok = ((lit < 15u ? lit : 15u) << 4) | (extra < 15u ? extra : 15u);
+        if (lit == 0u && extra < 15u + 255u) {             // token + offset (+ one length byte) in one go
+            uint64_t v = tok | ((uint64_t)dist << 8);
+            uint32_t k = 3u;
+            if (extra >= 15u) { v |= (uint64_t)(extra - 15u) << 24; k = 4u; }
+            out.put(v, k);
+            return;
+        }
+        out.put(tok, 1u);
+        if (lit >= 15u) put_len(lit - 15u);
+        for (uint32_t i = 0; i < lit; i += 8u) out.put(lits->rd8(anchor + i), lit - i < 8u ? lit - i : 8u);
+        out.put(dist, 2u);
+        if (extra >= 15u) put_len(extra - 15u);
+    }
+    TC_MFN void tail(uint32_t anchor, uint32_t n)
     {
         const uint32_t lit = n - anchor;
         out.put((lit < 15u ? lit : 15u) << 4, 1u);
-        if (lit >= 15u) {
-            uint32_t r = lit - 15u;
-            for (; r >= 255u; r -= 255u) out.put(0xffu, 1u);
-            out.put(r, 1u);
-        }
-        for (uint32_t i = 0; i < lit; i += 8u) out.put(cs.rd8(anchor + i), lit - i < 8u ? lit - i : 8u);
+        if (lit >= 15u) put_len(lit - 15u);
+        for (uint32_t i = 0; i < lit; i += 8u) out.put(lits->rd8(anchor + i), lit - i < 8u ? lit - i : 8u);
+        out.sync();
     }
-    out.sync();
-    return out.produced();
+};
+
+// K1-T: one block, one thread, straight to bytes.  Returns the compressed size.  The caller has checked
+// cap >= get_maximum_output_size(n) (compress.rs:338-340).
+template <typename TabT>
+TC_FN uint32_t encode_block_thread(const uint8_t *src, uint32_t n, uint8_t *dst, TabT *tab, bool cont, bool h5)
+{
+    Stream<true> in, cs;                       // cursor side / candidate side (cs also serves the literal copies)
+    in.init(src, n); cs.init(src, n);
+    DirectSink<Stream<true>> sink;
+    sink.out.init(dst);
+    sink.lits = &cs;
+    parse_block_thread<TabT>(in, cs, n, tab, cont, h5, sink);
+    return sink.out.produced();
 }
 
 // =============================================================================================

@@ -141,11 +141,14 @@ def block_error(status: int, expected: int = 0, actual: int = 0) -> Exception:
     return error_from_status(status)
 
 
-def error_from_status(status: int, block_status: int = 0, detail: str = "") -> Exception:
+def error_from_status(status: int, block_status: int = 0, detail: str = "", expected: int = 0,
+                      actual: int = 0) -> Exception:
     if 1 <= status <= 6:
-        return block_error(status)
+        return block_error(status, expected, actual)
     if status == 101:
-        return DecompressionError(block_error(block_status))
+        return DecompressionError(block_error(block_status, expected, actual))
+    if status == 109:
+        return ContentLengthError(expected, actual)
     if status in _FRAME:
         return _FRAME[status]()
     if status == 115:

@@ -23,7 +23,7 @@ from typing import Optional
 import numpy as np
 
 from . import _native, block as _block
-from .errors import (ContentLengthError, LinkedBlocksUnsupported, error_from_status)
+from .errors import (ContentChecksumError, ContentLengthError, IoError, LinkedBlocksUnsupported, error_from_status)
 
 WINDOW_SIZE = 64 * 1024
 _REPOSITION_LIMIT = 0xFFFFFFFF // 2          # u32::MAX as usize / 2  (frame/compress.rs:266)
@@ -121,23 +121,42 @@ def compress_frame(data, frame_info: FrameInfo | None = None, ctx: _block.Contex
     return out[: w.value].tobytes()
 
 
-def decompress_frame(data, ctx: _block.Context | None = None, partial: bool = False):
-    """FrameDecoder::new(data).read_to_end() — one C-ABI call over all concatenated frames.
-    With partial=True returns (bytes_before_error, exception_or_None) instead of raising."""
+def decompress_next_frame(data, ctx: _block.Context | None = None):
+    """The frame that starts at data[0], through lz4b200_frame_decompress_next: returns
+    (decoded bytes, consumed input bytes, exception or None).  Bytes decoded before an error are returned with it.
+    consumed == 0 with no bytes and no error means the input is exhausted (decompress.rs:113-128)."""
     ctx = ctx or _block.default_context()
     src = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    L = _native.lib()
     bound = C.c_size_t(0)
-    _native.lib().lz4b200_frame_decoded_bound(src.ctypes.data if src.size else None, src.size, C.byref(bound))
+    L.lz4b200_frame_decoded_bound(src.ctypes.data if src.size else None, src.size, C.byref(bound))
     out = np.empty(max(bound.value, 1), dtype=np.uint8)
-    w, bs = C.c_size_t(0), C.c_int(0)
-    st = _native.lib().lz4b200_frame_decompress(ctx.handle, src.ctypes.data if src.size else None, src.size,
-                                                out.ctypes.data, bound.value, C.byref(w), C.byref(bs))
-    err = None if st == 0 else error_from_status(st, bs.value, ctx.last_cuda_error())
+    used, w, bs = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+    e1, e2 = C.c_uint64(0), C.c_uint64(0)
+    st = L.lz4b200_frame_decompress_next(ctx.handle, src.ctypes.data if src.size else None, src.size, out.ctypes.data,
+                                         bound.value, C.byref(used), C.byref(w), C.byref(bs), C.byref(e1), C.byref(e2))
+    err = None if st == 0 else error_from_status(st, bs.value, ctx.last_cuda_error(), e1.value, e2.value)
+    return out[: w.value].tobytes(), used.value, err
+
+
+def decompress_frame(data, ctx: _block.Context | None = None, partial: bool = False):
+    """Every concatenated frame of `data`, outputs joined (a convenience; the reference's reader stops at each
+    EndMark — FrameDecoder below does too, and decompress_next_frame() exposes the boundaries).
+    With partial=True returns (bytes_before_error, exception_or_None) instead of raising."""
+    src = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    parts, pos, err = [], 0, None
+    while pos < src.size:
+        out, used, err = decompress_next_frame(src[pos:], ctx)
+        parts.append(out)
+        if err is not None or used == 0:
+            break
+        pos += used
+    joined = b"".join(parts)
     if partial:
-        return out[: w.value].tobytes(), err
+        return joined, err
     if err is not None:
         raise err
-    return out[: w.value].tobytes()
+    return joined
 
 
 # -----------------------------------------------------------------------------------------------------
@@ -329,17 +348,29 @@ class AutoFinishEncoder:
 class FrameDecoder(io.RawIOBase):
     """frame::FrameDecoder<R> (decompress.rs:48-422): a reader that decompresses LZ4 frames from `r`.
 
-    All concatenated frames of the underlying reader are decoded in one GPU batch at the first read();
-    bytes before a corrupt block are still delivered, and the error surfaces on the read that reaches it,
-    like the reference's block-at-a-time reader."""
+    Streaming with bounded memory, like the reference's block-at-a-time reader, but a GROUP of blocks at a time so the
+    GPU gets a batch: the header and the BlockInfo chain are read from `r` incrementally; blocks are collected until
+    their decoded bound reaches `group_bytes` (default 64 MiB) and then decoded in one C-ABI call.  Only one group of
+    compressed and decoded bytes is ever held.  (A frame with linked blocks is one dependency chain and is collected
+    whole.)  As in the reference, read() returns b"" at every EndMark (decompress.rs:310-331): read_to_end() returns the
+    rest of the CURRENT frame and the next call continues with the next frame (tests/tests.rs:633-647).  Bytes decoded
+    before a corrupt block are delivered first; the error surfaces on the read that reaches it."""
 
-    def __init__(self, r, ctx: _block.Context | None = None):
+    def __init__(self, r, ctx: _block.Context | None = None, group_bytes: int = 64 << 20):
         super().__init__()
         self.r = r
         self._ctx = ctx
-        self._buf: bytes | None = None
-        self._pos = 0
+        self._group_bytes = max(int(group_bytes), 1)
+        self._ready = bytearray()          # decoded, not yet handed out
         self._err: Exception | None = None
+        self._hdr: bytes | None = None     # header bytes of the frame being read (None: between frames)
+        self._bs = 0
+        self._flg = 0
+        self._content = None               # streaming XXH32 of the frame's content (if the header asks for it)
+        self._content_len = 0
+        self._content_size = None
+        self._eof = False                  # the underlying reader is exhausted
+        self._frame_done = False           # an EndMark was consumed: the next read() returns b"" once
 
     @classmethod
     def new(cls, r, **kw) -> "FrameDecoder":
@@ -357,25 +388,146 @@ class FrameDecoder(io.RawIOBase):
     def readable(self) -> bool:
         return True
 
+    # ---- underlying reader ----------------------------------------------------------------------------
+    def _read_upto(self, n: int) -> bytes:
+        """read_exact that tolerates short reads; returns fewer bytes only at the end of the reader."""
+        chunks, got = [], 0
+        while got < n:
+            c = self.r.read(n - got)
+            if not c:
+                break
+            chunks.append(bytes(c))
+            got += len(c)
+        return b"".join(chunks)
+
+    # ---- frame header: read_frame_info, decompress.rs:109-176 -------------------------------------------
+    def _read_header(self) -> bool:
+        """False = end of data where a frame would start."""
+        magic = self._read_upto(4)
+        if len(magic) == 0:
+            return False
+        if len(magic) < 4:
+            raise IoError("unexpected end of input in the magic number")
+        if magic == b"\x02\x21\x4c\x18":                                      # legacy frame, header.rs:285-291
+            self._hdr, self._bs, self._flg = magic, 8 << 20, 0x20
+        else:
+            rest = self._read_upto(3)
+            if len(rest) == 0:
+                return False                                                   # decompress.rs:124-128
+            if len(rest) < 3:
+                raise IoError("unexpected end of input in the frame header")
+            m = int.from_bytes(magic, "little")
+            if 0x184D2A50 <= m <= 0x184D2A5F:
+                raise error_from_status(111)
+            if m != 0x184D2204:
+                raise error_from_status(102)
+            flg = rest[0]
+            extra = (8 if flg & 0x08 else 0) + (4 if flg & 0x01 else 0)
+            more = self._read_upto(extra)
+            if len(more) < extra:
+                raise IoError("unexpected end of input in the frame header")
+            hdr = magic + rest + more
+            # validate exactly like the C walk does: decode the header as an empty frame
+            _, _, err = decompress_next_frame(hdr + b"\0\0\0\0" + (b"\0\0\0\0" if flg & 0x04 else b""), self._ctx)
+            if err is not None and not isinstance(err, (ContentLengthError, ContentChecksumError)):
+                raise err
+            self._hdr, self._flg = hdr, flg
+            self._bs = {4: 64 << 10, 5: 256 << 10, 6: 1 << 20, 7: 4 << 20}[(rest[1] >> 4) & 7]
+            self._content_size = int.from_bytes(more[:8], "little") if flg & 0x08 else None
+        self._content = _Xxh32(0) if self._flg & 0x04 else None
+        self._content_len = 0
+        return True
+
+    # ---- one group of blocks: read_block, decompress.rs:189-342 ------------------------------------------
     def _fill(self):
-        if self._buf is None:
-            data = self.r.read()
-            self._buf, self._err = decompress_frame(data, self._ctx, partial=True) if data else (b"", None)
+        """Decode the next group of blocks of the current frame into self._ready (may set self._err / _frame_done)."""
+        if self._hdr is None:
+            if self._eof or not self._read_header():
+                self._eof = True
+                return
+        linked = not (self._flg & 0x20)
+        has_bc = bool(self._flg & 0x10)
+        body, bound, closed, end_err = [], 0, False, None
+        while linked or bound < self._group_bytes or not body:
+            w = self._read_upto(4)
+            if len(w) < 4:                                                      # EOF where a BlockInfo is due: Ok(0)
+                self._eof = True
+                break
+            word = int.from_bytes(w, "little")
+            if word == 0:
+                closed = True
+                break
+            ln = word & 0x7FFFFFFF
+            if ln > self._bs:
+                end_err = error_from_status(110)
+                break
+            payload = self._read_upto(ln + (4 if has_bc else 0))
+            if len(payload) < ln + (4 if has_bc else 0):
+                end_err = IoError("unexpected end of input inside a block")
+                self._eof = True
+                break
+            body.append(w + payload)
+            bound += ln if word & 0x80000000 else min(self._bs, 255 * ln + 16)
+        if body:
+            # the group as a frame of its own: same block size / block-checksum / linkage flags, no content size or checksum
+            if len(self._hdr) == 4:                                             # legacy frame: magic + blocks, no EndMark
+                group = self._hdr + b"".join(body)
+            else:
+                mini_hdr = bytes([(self._flg & 0x30) | 0x40, self._hdr[5]])
+                group = (b"\x04\x22\x4d\x18" + mini_hdr + bytes([(xxh32(mini_hdr) >> 8) & 0xFF]) + b"".join(body)
+                         + b"\0\0\0\0")
+            out, _, err = decompress_next_frame(group, self._ctx)
+            self._ready += out
+            self._content_len += len(out)
+            if self._content is not None:
+                self._content.update(out)
+            if err is not None:
+                self._err = err
+                self._hdr = None
+                return
+        if end_err is not None:
+            self._err = end_err
+            self._hdr = None
+            return
+        if closed:
+            err = None
+            if self._content_size is not None and self._content_len != self._content_size:
+                err = ContentLengthError(self._content_size, self._content_len)                 # decompress.rs:312-321
+            if self._flg & 0x04:
+                c = self._read_upto(4)
+                if len(c) < 4:
+                    err = err or IoError("unexpected end of input in the content checksum")
+                elif err is None and int.from_bytes(c, "little") != self._content.digest():
+                    err = ContentChecksumError()
+            self._hdr = None
+            self._frame_done = True
+            self._err = err
+        elif self._eof:
+            self._hdr = None
 
     def read(self, size: int = -1) -> bytes:
-        self._fill()
-        if self._pos >= len(self._buf):
-            if self._err is not None:
+        want_all = size is None or size < 0
+        while (want_all or len(self._ready) < size) and self._err is None and not self._frame_done:
+            if self._eof and self._hdr is None:
+                break
+            self._fill()
+        if self._ready:
+            n = len(self._ready) if want_all else min(size, len(self._ready))
+            out = bytes(self._ready[:n])
+            del self._ready[:n]
+            if want_all and self._err is not None:
                 e, self._err = self._err, None
-                raise e
-            return b""
-        end = len(self._buf) if size is None or size < 0 else min(len(self._buf), self._pos + size)
-        out = self._buf[self._pos:end]
-        self._pos = end
-        if (size is None or size < 0) and self._err is not None:
+                self._frame_done = False
+                raise _with_partial(e, out)
+            if want_all:
+                self._frame_done = False
+            return out
+        if self._err is not None:
             e, self._err = self._err, None
+            self._frame_done = False
             raise e
-        return out
+        self._frame_done = False                                                # the b"" of this EndMark
+        return b""
 
     def readinto(self, b) -> int:
         data = self.read(len(b))
@@ -383,4 +535,15 @@ class FrameDecoder(io.RawIOBase):
         return len(data)
 
     def read_to_end(self) -> bytes:
+        """Read::read_to_end: the rest of the current frame (empty at the end of the data)."""
         return self.read(-1)
+
+
+def _with_partial(e: Exception, partial: bytes) -> Exception:
+    """read(-1) that hits an error after delivering bytes: the bytes travel on the exception (`.partial`), like the
+    Vec a failed read_to_end leaves filled in the reference."""
+    try:
+        e.partial = partial
+    except Exception:
+        pass
+    return e

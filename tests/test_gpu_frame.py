@@ -65,7 +65,13 @@ def test_frame_encoder_write_patterns(ctx):
     enc.write(data[:200000]); enc.try_finish()
     enc.write(data[200000:]); enc.try_finish()
     assert sink.getvalue() == oracle.frame_compress(data[:200000], 4) + oracle.frame_compress(data[200000:], 4)
-    assert FrameDecoder(io.BytesIO(sink.getvalue()), ctx).read() == data      # concatenated (tests.rs:633-647)
+    dec = FrameDecoder(io.BytesIO(sink.getvalue()), ctx)                      # concatenated frames: tests.rs:633-647 —
+    assert dec.read_to_end() == data[:200000]                                 # read_to_end stops at each EndMark
+    assert dec.read_to_end() == data[200000:]
+    assert dec.read_to_end() == b""
+    assert frame.decompress_frame(sink.getvalue(), ctx) == data               # the join-all convenience
+    out1, used1, err1 = frame.decompress_next_frame(sink.getvalue(), ctx)     # C ABI: one frame per call + consumed bytes
+    assert (out1, err1) == (data[:200000], None) and used1 == len(oracle.frame_compress(data[:200000], 4))
     with FrameEncoder(io.BytesIO(), FrameInfo(block_size=BlockSize.Max64KB), ctx).auto_finish() as af:
         af.write(data[:5000])
         inner = af.encoder.get_ref()
@@ -116,6 +122,89 @@ def test_frame_decoder_reads_and_errors(ctx):
         assert err is None and out == eo
     else:
         assert isinstance(err, errors.DecompressionError) and out[:65536] == d[:65536]
+
+
+def test_frame_decoder_content_length_and_partial_delivery(ctx):
+    """A header whose content_size is SMALLER than the real content: every byte is still delivered, then
+    ContentLengthError{expected, actual} (decompress.rs:312-321) — the bound must not trust the header."""
+    a = corpus.load("compression_34k.txt")
+    f = bytearray(oracle.frame_compress(a, 4, oracle.F_CONTENT_SIZE))
+    assert int.from_bytes(f[6:14], "little") == len(a)
+    f[6:14] = (100).to_bytes(8, "little")
+    f[14] = (frame.xxh32(bytes(f[4:14])) >> 8) & 0xFF                        # re-seal the header checksum
+    out, used, err = frame.decompress_next_frame(bytes(f), ctx)
+    assert out == a and used == len(f)
+    assert isinstance(err, errors.ContentLengthError) and (err.expected, err.actual) == (100, len(a))
+    dec = FrameDecoder(io.BytesIO(bytes(f)), ctx)
+    got = bytearray()
+    with pytest.raises(errors.ContentLengthError) as e:
+        while True:
+            p = dec.read(7000)
+            if not p:
+                break
+            got += p
+    assert bytes(got) == a and (e.value.expected, e.value.actual) == (100, len(a))
+    # larger than the real content
+    f[6:14] = (10**9).to_bytes(8, "little")
+    f[14] = (frame.xxh32(bytes(f[4:14])) >> 8) & 0xFF
+    out, used, err = frame.decompress_next_frame(bytes(f), ctx)
+    assert out == a and (err.expected, err.actual) == (10**9, len(a))
+    # a block that needs more than its frame's block size: OutputTooSmall{expected, actual} inside DecompressionError
+    big = oracle.compress_block(bytes(70000))
+    g = bytes([4, 0x22, 0x4D, 0x18, 0x60, 0x40, 0x82]) + len(big).to_bytes(4, "little") + big + b"\0\0\0\0"
+    out, used, err = frame.decompress_next_frame(g, ctx)
+    assert isinstance(err, errors.DecompressionError) and isinstance(err.inner, errors.OutputTooSmall)
+    assert err.inner.actual == 65536 and err.inner.expected > 65536
+    # end-of-data conventions of read_frame_info (decompress.rs:113-128)
+    assert frame.decompress_next_frame(b"", ctx) == (b"", 0, None)
+    assert frame.decompress_next_frame(b"\x04\x22\x4d\x18", ctx) == (b"", 4, None)
+    assert isinstance(frame.decompress_next_frame(b"\x04\x22", ctx)[2], errors.IoError)
+
+
+def test_frame_decoder_bounded_memory(ctx):
+    """20 000 tiny blocks in a 4 MiB-block frame (a FrameEncoder stream with frequent flush()): decoded with a device
+    budget far below #blocks x block size, in several groups, byte-exact; and streamed through FrameDecoder in small
+    groups from a reader that returns short reads."""
+    from lz4_flex_b200 import _native
+    data = corpus.tiled("compression_66k_JSON.txt", 20000 * 150).tobytes()
+    f = oracle.frame_compress(data, 7, oracle.F_CONTENT_CHECKSUM, 150)      # flush every 150 bytes
+    bound = ctypes_size()
+    _native.lib().lz4b200_frame_decoded_bound(f, len(f), bound)
+    assert bound.value < 64 * len(data)                                      # not 20 000 x 4 MiB
+    _native.lib().lz4b200_ctx_set_frame_budget(ctx.handle, 1 << 20)
+    try:
+        assert frame.decompress_frame(f, ctx) == data
+    finally:
+        _native.lib().lz4b200_ctx_set_frame_budget(ctx.handle, 256 << 20)
+
+    class Dribble(io.RawIOBase):
+        def __init__(self, b):
+            self.b, self.p, self.k = b, 0, 0
+        def readable(self):
+            return True
+        def read(self, n=-1):
+            self.k += 1
+            n = len(self.b) - self.p if n is None or n < 0 else min(n, 1 + self.k % 977)
+            out = self.b[self.p:self.p + n]
+            self.p += len(out)
+            return out
+
+    big = corpus.tiled("dickens.txt", 5 << 20).tobytes()
+    ff = oracle.frame_compress(big, 4, 7) + f
+    dec = FrameDecoder(Dribble(ff), ctx, group_bytes=1 << 20)
+    assert dec.read_to_end() == big
+    got = bytearray()
+    while True:
+        p = dec.read(100000)
+        if not p:
+            break
+        got += p
+    assert bytes(got) == data and dec.read() == b""
+
+
+def ctypes_size():
+    import ctypes
+    return ctypes.c_size_t(0)
 
 
 def test_legacy_frame_fixture(ctx):

@@ -30,6 +30,8 @@ def tch():
     L = C.CDLL(SO)
     L.tc_host_compress.restype = C.c_uint32
     L.tc_host_compress.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    L.tc_host_compress_solo.restype = C.c_uint32
+    L.tc_host_compress_solo.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     L.tc_host_decompress.restype = C.c_int
     L.tc_host_decompress.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     return L
@@ -38,18 +40,19 @@ def tch():
 def _place(data: bytes, mis: int):
     """data inside a padded array at byte misalignment `mis` (the codec reads whole aligned words that overlap the
     buffer, so 8 bytes of slack either side keep a host build inside one allocation)."""
-    a = np.full(len(data) + 32, 0xA5, dtype=np.uint8)
+    a = np.full(len(data) + 64, 0xA5, dtype=np.uint8)
     base = a.ctypes.data
-    off = (8 - base % 8) % 8 + 8 + mis
+    off = (16 - base % 16) % 16 + 16 + mis
     a[off:off + len(data)] = np.frombuffer(data, dtype=np.uint8)
     return a, off
 
 
-def t_compress(tch, data: bytes, flags=0, mis_in=0, mis_out=0) -> bytes:
+def t_compress(tch, data: bytes, flags=0, mis_in=0, mis_out=0, solo=False) -> bytes:
     a, ao = _place(data, mis_in)
     cap = oracle.max_output_size(len(data))
     o, oo = _place(bytes(cap), mis_out)
-    n = tch.tc_host_compress(a.ctypes.data + ao, len(data), o.ctypes.data + oo, flags)
+    fn = tch.tc_host_compress_solo if solo else tch.tc_host_compress
+    n = fn(a.ctypes.data + ao, len(data), o.ctypes.data + oo, flags)
     assert n <= cap
     assert (o[:oo] == 0xA5).all(), "bytes before the output were modified"
     assert (o[oo + cap:] == 0xA5).all(), "bytes after the output slot were modified"
@@ -216,3 +219,32 @@ def test_decode_foreign_and_big(tch):
     for mo in range(8):
         st, o, _ = t_decompress(tch, cz, 65536, 0, mo)
         assert st == 0 and o == z
+
+
+# ---- K1-S: the same parse over the shared-memory ring views (host ring, memcpy for the TMA) -----------------------------
+
+def test_solo_ring_parse_matches_oracle(tch):
+    """Slot reuse, look-ahead and the 64 KiB history bound of lz4b200_solo_ring.cuh: a slot overwritten too early would
+    change the parse.  4 MiB blocks (1 024 ring laps), far matches (distance close to 65 535), long matches that run the
+    cursor far ahead, long backward extensions that reach behind the ring, every input misalignment mod 16."""
+    rng = np.random.default_rng(123)
+    h, d = corpus.load("hdfs.json"), corpus.load("dickens.txt")
+    cases = [h[: 4 << 20], d[: 4 << 20], d[5: 5 + (1 << 20)], h[3: 3 + 70000], bytes(300000), corpus.load("compression_66k_JSON.txt")]
+    # far matches: a random page repeated at distances around the 65 535 limit
+    page = bytes(rng.integers(0, 256, 4096, dtype=np.uint8))
+    for gap in (65535 - 4096 - 8, 65535 - 4096, 65536 - 4096, 65540 - 4096, 60000):
+        cases.append((page + bytes(rng.integers(0, 256, gap, dtype=np.uint8))) * 4)
+    # long backward extension: literal run that matches backwards for several KiB once a 4-byte match is found late
+    blob = bytes(rng.integers(0, 256, 70000, dtype=np.uint8))
+    cases.append(blob + b"#" + blob[1:] )                      # second copy found late => backtrack
+    cases.append(blob[:30000] + bytes(200000) + blob[:30000] + bytes(1000))
+    for i, data in enumerate(cases):
+        for flags, want in oracle_modes(data).items():
+            assert t_compress(tch, data, flags, solo=True) == want, (i, len(data), flags)
+    data = h[: 200000]
+    want = oracle.compress_block_cont(data)
+    for mi in range(16):
+        assert t_compress(tch, data, CONT | H5, mi, 0, solo=True) == want, mi
+    for n in list(range(0, 40)) + [2047, 2048, 2049, 2048 * 40 - 1, 2048 * 40, 2048 * 40 + 17]:
+        data = (d[:n])
+        assert t_compress(tch, data, 0, 5, 0, solo=True) == oracle.compress_block(data), n
