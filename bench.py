@@ -317,6 +317,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # bind this rank (and the pinned staging buffers it allocates from here on) to its GPU's NUMA node
+    from lz4_flex_b200 import numa
+    ninfo = numa.bind_to_gpu_node(local)
+    numa_rec = {k: v for k, v in ninfo.items() if k != "original_affinity"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -485,6 +489,13 @@ def run_ours(args):
     h2d = nb * BLOCK + comp_bytes + 2 * desc_bytes
     d2h = comp_bytes + nb * BLOCK + nb * (4 + 4 + 8) + nb * (4 + 4 + 8)
 
+    # ---- the multi-GPU path of the north star (BASELINE config 4), measured at every N as a second record ----------
+    del d_comp, d_back, h_comp, h_back
+    torch.cuda.empty_cache()
+    frame_rec = None
+    if not args.no_frame:
+        frame_rec = measure_sharded_frame(args, ctx, dev, rank, world, numa_rec)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -500,7 +511,10 @@ def run_ours(args):
     ach_c = alg_bytes / (t_c / 1e3) / 1e9
     ach_d = alg_bytes / (t_d / 1e3) / 1e9
 
-    # CPU baseline on this box's host cores: the whole batch, persistent pool
+    # CPU baseline on this box's host cores: the whole batch, persistent pool (all cores: undo the NUMA binding first)
+    numa.restore_affinity(ninfo)
+    if frame_rec is not None:
+        frame_rec["cpu_baseline"] = cpu_frame_baseline(8)
     threads, cores = host_topology()
     # the CPU baseline is timed on rank 0 at N=1 only (the other ranks' host pipelines would compete for the cores)
     cpu_all = cpu_arm(data, nb, threads, 3) if world == 1 else None
@@ -544,69 +558,174 @@ def run_ours(args):
                           f"host threads / two contexts")},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
+        "numa": numa_rec,
+        "sharded_frame": frame_rec,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_frame(args):
-    """Config 4: one LZ4 frame of 4 MiB independent blocks over hdfs.json log data, the blocks sharded
-    over the ranks (256 per GPU: weak scaling), compressed chunks gathered to rank 0 over NCCL.  One step =
-    compress this rank's block range + the gather; value = uncompressed MiB/s of the whole job."""
+def hdfs_range(lo: int, n: int) -> np.ndarray:
+    """Bytes [lo, lo + n) of hdfs.json tiled by ABSOLUTE offset (BASELINE config 4)."""
+    from lz4_flex_b200 import corpus
+    src = np.frombuffer(corpus.load("hdfs.json"), dtype=np.uint8)
+    i0 = lo % src.size
+    reps = -(-(n + i0) // src.size)
+    return np.ascontiguousarray(np.tile(src, reps)[i0: i0 + n])
+
+
+def oracle_frame_from(first_block: int, data: np.ndarray, bs: int) -> bytes:
+    """Oracle frame body+header for blocks [first_block, ...) of a 4 MiB-block stream: the reference's persistent table
+    driven from the same stream offset (frame/compress.rs:261-371; table epochs per :266-271)."""
+    import oracle
+    from lz4_flex_b200.frame import BlockSize, FrameInfo
+    table = oracle.FrameTable()
+    table.offset = first_block * bs
+    out = [FrameInfo(block_size=BlockSize.Max4MB).header_bytes()]
+    for k in range(0, data.size, bs):
+        blk = data[k:k + bs].tobytes()
+        c = table.compress(blk, bs)
+        out.append(len(c).to_bytes(4, "little") + c if len(c) < len(blk) else (len(blk) | 0x80000000).to_bytes(4, "little") + blk)
+    out.append(b"\0\0\0\0")
+    return b"".join(out)
+
+
+def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
+    """BASELINE config 4, the multi-GPU path the north star names: ONE LZ4 frame of 4 MiB independent blocks over
+    hdfs.json log data tiled by absolute offset, `--frame-blocks` (256) blocks per GPU, block modes by absolute index
+    (FRESH at 0, 511, 1022, ...), every rank compresses its contiguous block range and the packed chunks are gathered
+    into rank 0's frame buffer INSIDE the timed step (sizes all_gather + pack kernels storing over NVLink + completion
+    all_reduce; lz4_flex_b200.sharded.PeerFrameGather).  Returns the record (rank 0) or None."""
+    import hashlib
     import torch
     import torch.distributed as dist
-    from lz4_flex_b200 import block, corpus, sharded
-    from lz4_flex_b200.frame import BlockSize, FrameInfo
+    from lz4_flex_b200 import sharded
 
+    bs = 4 << 20
+    per = args.frame_blocks
+    total = world * per * bs
+    mine = hdfs_range(rank * per * bs, per * bs)
+    h_in = torch.empty(per * bs, dtype=torch.uint8).pin_memory()
+    h_in.numpy()[:] = mine
+    d_in = h_in.to(dev, non_blocking=True)
+
+    # ---- parity on a reduced config that crosses the table-epoch boundary: blocks 508.. (6 per rank) vs the oracle ----
+    pb = 6
+    base = 508
+    small = hdfs_range((base + rank * pb) * bs, pb * bs)
+    g = sharded.PeerFrameGather(world * pb * bs, 7, rank, world, ctx, base_block=base)
+    g.step(torch.from_numpy(small).to(dev))
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        got = g.result().cpu().numpy().tobytes()
+        want = oracle_frame_from(base, hdfs_range(base * bs, world * pb * bs), bs)
+        parity = {"blocks": world * pb, "first_block": base, "fresh_block_inside": 511,
+                  "frame_sha256": hashlib.sha256(got).hexdigest(), "oracle_sha256": hashlib.sha256(want).hexdigest(),
+                  "byte_identical_to_oracle": got == want}
+    g.close()
+
+    # ---- the timed workload ------------------------------------------------------------------------------------------
+    g = sharded.PeerFrameGather(total, 7, rank, world, ctx)
+    for _ in range(max(args.warmup, 3)):
+        g.step(d_in)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(1, min(args.steps, 10))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    kms, xms = [], []
+    e0.record()
+    for _ in range(steps):
+        g.step(d_in, timed=True)
+    e1.record()
+    torch.cuda.synchronize()
+    # per-phase times of the last step (events inside the step); whole-step time from the outer pair
+    k_ms, x_ms = g.timings_ms()
+    ms = e0.elapsed_time(e1) / steps
+    # ---- end to end: host buffer -> H2D -> compress -> gather -> frame on rank 0's host ---------------------------------
+    frame_len = int(g.frame_len.item()) if rank == 0 else 0
+    h_frame = torch.empty(max(frame_len, 1), dtype=torch.uint8).pin_memory() if rank == 0 else None
+    e2e = []
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d_in.copy_(h_in, non_blocking=True)
+        g.step(d_in)
+        if rank == 0:
+            h_frame.copy_(g.frame[:frame_len], non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        if it:
+            e2e.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e))
+    t = torch.tensor([ms, k_ms, x_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, k_ms, x_ms, e2e_s = [float(v) for v in t.cpu()]
+    rec = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        comp_bytes = frame_len
+        alg = per * bs + comp_bytes / world                      # per GPU: input read + its share of the frame written
+        rec = {
+            "workload": f"BASELINE config 4: {world * per} x 4 MiB hdfs.json blocks ({total / 2**30:.0f} GiB), frame format, "
+                        f"{per} blocks per GPU, block modes by absolute index, gathered into rank 0's frame buffer",
+            "value": total / 2**20 / (ms / 1e3), "unit": "MiB/s", "ms_per_step": ms, "steps": steps,
+            "scaling": "weak", "frame_bytes": frame_len, "ratio": frame_len / total,
+            "collective": {"compress_kernel_ms": k_ms, "exchange_and_pack_ms": x_ms,
+                           "how": "all_gather of 8-byte sizes, device prefix sum, pack kernel storing into rank 0's "
+                                  "buffer over NVLink (CUDA IPC mapping), 4-byte all_reduce as completion; no host sync"},
+            "roofline": {"kernel": "lz4_compress_blocks_solo", "bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+            "e2e": {"value": total / 2**20 / e2e_s, "unit": "MiB/s", "ms_per_step": 1e3 * e2e_s,
+                    "h2d_bytes_per_step": per * bs, "d2h_bytes_per_step": frame_len,
+                    "api": "pinned host range -> H2D -> lz4b200_frame_range_compress -> size exchange -> "
+                           "lz4b200_frame_range_pack into rank 0 -> D2H of the frame"},
+            "parity": parity, "numa": numa_info,
+        }
+    g.close()
+    return rec
+
+
+def cpu_frame_baseline(nblocks: int):
+    """The reference's frame path is ONE thread per frame (FrameEncoder is a single &mut self stream): the CPU port
+    compressing `nblocks` 4 MiB hdfs blocks of the frame on one thread."""
+    import oracle
+    bs = 4 << 20
+    data = hdfs_range(0, nblocks * bs)
+    t0 = time.perf_counter()
+    f = oracle.frame_compress(data, 7)
+    dt = time.perf_counter() - t0
+    return {"value": nblocks * bs / 2**20 / dt, "unit": "MiB/s", "cores": 1, "kind": "port",
+            "sample": f"{nblocks} x 4 MiB blocks of the same stream, one thread (the reference's FrameEncoder is serial per frame)",
+            "ratio": len(f) / (nblocks * bs)}
+
+
+def run_frame(args):
+    """--workload frame: only the sharded-frame measurement (the default bench line carries it as `sharded_frame`)."""
+    import torch
+    import torch.distributed as dist
+    from lz4_flex_b200 import block, numa
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ninfo = numa.bind_to_gpu_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    bs = 4 << 20
-    per = args.frame_blocks
-    total = world * per * bs
-    src = np.frombuffer(corpus.load("hdfs.json"), dtype=np.uint8)
-    lo = rank * per * bs
-    idx0 = lo % src.size
-    reps = -(-(per * bs + idx0) // src.size)
-    mine = np.ascontiguousarray(np.tile(src, reps)[idx0: idx0 + per * bs])
-    d_in = torch.from_numpy(mine).to(dev)
     ctx = block.Context(local)
-    info = FrameInfo(block_size=BlockSize.Max4MB)
-
-    def step():
-        part, d_total = sharded.compress_range_device(d_in, bs, rank * per, ctx)
-        n = int(d_total.item())
-        return sharded.gather_frame(part, n, info, rank, world), n
-
-    for _ in range(max(args.warmup, 1)):
-        fr, n = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        fr, n = step()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.cpu()[0])
+    rec = measure_sharded_frame(args, ctx, dev, rank, world, {k: v for k, v in ninfo.items() if k != "original_affinity"})
     if rank == 0:
-        ok = None
-        if world * per <= 64:                         # small enough to check the whole frame against the oracle
-            import oracle
-            full = np.tile(src, -(-total // src.size))[:total]
-            ok = fr.cpu().numpy().tobytes() == oracle.frame_compress(full, 7)
-        print(json.dumps({"metric": "LZ4 frame compress MiB/s, 4 MiB independent blocks sharded over ranks + NCCL gather",
-                          "value": total / 2**20 / (ms / 1e3), "unit": "MiB/s", "n_gpus": world, "steps": args.steps,
-                          "ms_per_step": ms, "scaling": "weak", "frame_bytes": int(fr.numel()),
-                          "ratio": int(fr.numel()) / total, "byte_identical_to_oracle": ok,
-                          "config": {"workload": f"{world * per} x 4 MiB hdfs.json blocks, frame format, {per} per GPU"}}))
+        numa.restore_affinity(ninfo)
+        rec["cpu_baseline"] = cpu_frame_baseline(8)
+        rec["n_gpus"] = world
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
@@ -621,7 +740,8 @@ def main():
     ap.add_argument("--quick", action="store_true", help="kernel timings only (tuning aid; not a bench line)")
     ap.add_argument("--workload", default="blocks", choices=["blocks", "frame"],
                     help="blocks = BASELINE config 2 (default); frame = config 4 sharded frame + NCCL gather")
-    ap.add_argument("--frame-blocks", type=int, default=256, help="4 MiB blocks per GPU for --workload frame")
+    ap.add_argument("--frame-blocks", type=int, default=256, help="4 MiB blocks per GPU for the sharded-frame record")
+    ap.add_argument("--no-frame", action="store_true", help="skip the sharded-frame record (tuning aid)")
     args = ap.parse_args()
     if args.workload == "frame" and args.impl == "ours":
         run_frame(args)

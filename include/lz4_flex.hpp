@@ -483,6 +483,10 @@ private:
 
 // frame::FrameDecoder<R> (decompress.rs:48-422) over an in-memory source: decodes every concatenated frame in one
 // GPU batch at the first read; bytes before a corrupt block are delivered before the error surfaces.
+// frame::FrameDecoder<R> over an in-memory stream (decompress.rs:48-422).  Like the reference, read() returns 0 at
+// every EndMark and read_to_end() returns the rest of the CURRENT frame: a second read_to_end() continues with the next
+// concatenated frame (tests/tests.rs:633-647).  One frame at a time is decoded (lz4b200_frame_decompress_next), so the
+// memory held is one frame's output, and the device memory behind it is bounded by the context's frame budget.
 class FrameDecoder {
 public:
     FrameDecoder(const uint8_t *data, size_t n, lz4b200_ctx *ctx = nullptr) : data_(data), n_(n), ctx_(ctx) {}
@@ -491,8 +495,9 @@ public:
     Result<size_t, Error> read(uint8_t *buf, size_t len)
     {
         using R = Result<size_t, Error>;
-        fill();
+        if (pos_ >= out_.size() && !at_frame_end_) next_frame();
         if (pos_ >= out_.size()) {
+            at_frame_end_ = false;                             // the Ok(0) of this EndMark / the end of the data
             if (err_.status != LZ4B200_OK) { Error e = err_; err_ = Error(); return R::Err(e); }
             return R::Ok(0);
         }
@@ -502,42 +507,51 @@ public:
         return R::Ok(take);
     }
 
-    // read_to_end
+    // read_to_end: the rest of the current frame (bytes decoded before an error are lost to the caller, as with the
+    // reference's Vec on Err — use read() to drain them first)
     Result<std::vector<uint8_t>, Error> read_to_end()
     {
         using R = Result<std::vector<uint8_t>, Error>;
-        fill();
-        if (err_.status != LZ4B200_OK) return R::Err(err_);
+        if (pos_ >= out_.size() && !at_frame_end_) next_frame();
+        at_frame_end_ = false;
+        if (err_.status != LZ4B200_OK) { Error e = err_; err_ = Error(); pos_ = out_.size(); return R::Err(e); }
         std::vector<uint8_t> rest(out_.begin() + (long)pos_, out_.end());
         pos_ = out_.size();
         return R::Ok(std::move(rest));
     }
 
 private:
-    void fill()
+    void next_frame()
     {
-        if (filled_) return;
-        filled_ = true;
+        out_.clear(); pos_ = 0;
+        if (ip_ >= n_) return;
         lz4b200_ctx *ctx = ctx_ ? ctx_ : default_context();
         if (!ctx) { err_.status = LZ4B200_CUDA_ERROR; return; }
-        size_t bound = 0, written = 0;
-        lz4b200_frame_decoded_bound(data_, n_, &bound);
+        size_t bound = 0, written = 0, used = 0;
+        lz4b200_frame_decoded_bound(data_ + ip_, n_ - ip_, &bound);          // all remaining frames: an upper bound
         out_.resize(bound ? bound : 1);
         int block_status = 0;
-        const lz4b200_status st = lz4b200_frame_decompress(ctx, data_, n_, out_.data(), bound, &written, &block_status);
+        uint64_t e1 = 0, e2 = 0;
+        const lz4b200_status st = lz4b200_frame_decompress_next(ctx, data_ + ip_, n_ - ip_, out_.data(), bound, &used, &written,
+                                                                &block_status, &e1, &e2);
         out_.resize(written);
+        ip_ = (st == LZ4B200_OK && used) ? ip_ + used : n_;                  // an error ends the stream
+        at_frame_end_ = written != 0;
         if (st != LZ4B200_OK) {
             err_.status = st;
-            if (st == LZ4B200_FRAME_DECOMPRESSION_ERROR)
+            err_.expected = e1; err_.actual = e2;
+            if (st == LZ4B200_FRAME_DECOMPRESSION_ERROR) {
                 err_.decompression_error.kind = (block::DecompressError::Kind)block_status;
+                err_.decompression_error.expected = e1; err_.decompression_error.actual = e2;
+            }
         }
     }
     const uint8_t *data_;
     size_t n_;
     lz4b200_ctx *ctx_;
     std::vector<uint8_t> out_;
-    size_t pos_ = 0;
-    bool filled_ = false;
+    size_t pos_ = 0, ip_ = 0;
+    bool at_frame_end_ = false;
     Error err_;
 };
 

@@ -277,6 +277,23 @@ lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx,
     const uint8_t *d_in, size_t in_len, size_t block_size, uint64_t first_block,
     uint8_t *d_out, size_t out_cap, uint64_t *d_total, uint32_t *d_block_sizes, void *stream);
 
+/* The same work in two steps, for the sharded (multi-GPU) frame path of SURVEY.md §8e: _range_compress leaves the
+ * range's compressed / stored blocks in the context and writes the packed size to *d_total (device); _range_pack lays
+ * the [BlockInfo | payload] segments out at d_dst + *d_dst_offset (device scalar; NULL = 0).  d_dst may be PEER
+ * memory — rank 0's frame buffer mapped with lz4b200_peer_open — so the pack kernel's stores are the NVLink transfer of
+ * the gather step (frame/compress.rs:261-371 writes the same bytes to its io::Write in block order). */
+lz4b200_status lz4b200_frame_range_compress(lz4b200_ctx *ctx, const uint8_t *d_in, size_t in_len, size_t block_size,
+                                            uint64_t first_block, uint64_t *d_total, uint32_t *d_block_sizes,
+                                            void *stream);
+lz4b200_status lz4b200_frame_range_pack(lz4b200_ctx *ctx, uint8_t *d_dst, const uint64_t *d_dst_offset, void *stream);
+
+/* Buffers shared between the ranks of one node (CUDA IPC, one process per GPU): the owner allocates and gets a
+ * 64-byte handle to pass around (any transport); the others map it and may hand the mapping to _range_pack. */
+lz4b200_status lz4b200_peer_alloc(lz4b200_ctx *ctx, size_t bytes, void **d_ptr, uint8_t *handle64);
+lz4b200_status lz4b200_peer_open(lz4b200_ctx *ctx, const uint8_t *handle64, void **d_ptr);
+lz4b200_status lz4b200_peer_close(lz4b200_ctx *ctx, void *d_ptr);
+lz4b200_status lz4b200_peer_free(lz4b200_ctx *ctx, void *d_ptr);
+
 /* Bytes of scratch-free output space the call above needs in the worst case. */
 size_t lz4b200_frame_blocks_bound(size_t in_len, size_t block_size);
 

@@ -112,6 +112,12 @@ SIGNATURES = {
     "lz4b200_frame_compress": (_i32, [_vp, _vp, _sz, C.POINTER(FrameInfoC), _sz, _vp, _sz, _psz]),
     "lz4b200_frame_compress_blocks_device": (_i32, [_vp, _vp, _sz, _sz, C.c_uint64, _vp, _sz, _vp, _vp, _vp]),
     "lz4b200_frame_blocks_bound": (_sz, [_sz, _sz]),
+    "lz4b200_frame_range_compress": (_i32, [_vp, _vp, _sz, _sz, C.c_uint64, _vp, _vp, _vp]),
+    "lz4b200_frame_range_pack": (_i32, [_vp, _vp, _vp, _vp]),
+    "lz4b200_peer_alloc": (_i32, [_vp, _sz, C.POINTER(_vp), _vp]),
+    "lz4b200_peer_open": (_i32, [_vp, _vp, C.POINTER(_vp)]),
+    "lz4b200_peer_close": (_i32, [_vp, _vp]),
+    "lz4b200_peer_free": (_i32, [_vp, _vp]),
     "lz4b200_frame_write_header": (_sz, [C.POINTER(FrameInfoC), _vp, _sz]),
     "lz4b200_frame_decompress": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz, C.POINTER(C.c_int)]),
     "lz4b200_frame_decoded_bound": (_i32, [_vp, _sz, _psz]),

@@ -74,6 +74,7 @@ struct GatherArgs {
     uint8_t *dst;
     const uint64_t *dst_off;
     uint32_t nseg;
+    const uint64_t *dst_shift = nullptr;   // optional device scalar added to every destination offset
 };
 
 __global__ void __launch_bounds__(256) gather_segments_kernel(GatherArgs g)
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) gather_segments_kernel(GatherArgs g)
         const bool second = g.pick && g.pick[b];
         const uint8_t *s = second ? g.src_b + g.off_b[b] : g.src_a + g.off_a[b];
         const uint32_t len = second ? g.len_b[b] : g.len_a[b];
-        uint8_t *d = g.dst + g.dst_off[b];
+        uint8_t *d = g.dst + g.dst_off[b] + (g.dst_shift ? *g.dst_shift : 0ull);
         if (g.prefix_word) {
             if (threadIdx.x < 4) d[threadIdx.x] = (uint8_t)(g.prefix_word[b] >> (8 * threadIdx.x));
             d += 4;
@@ -261,6 +262,9 @@ struct lz4b200_ctx {
     int enc_gtab_carveout = -1;               // LZ4B200_ENC_GTAB_CARVEOUT=<percent of shared memory>
     bool enc_gtab_carveout_set = false;
     DevBuf<uint16_t> d_gtab16;
+    DevBuf<uint32_t> d_gtag32;                // tagged global tables (lz4_compress_blocks_gtag)
+    int enc_gtag = 71;                        // LZ4B200_ENC_GTAG=10*matchers+emitters (71|62), 0: untagged gtab kernel
+    int enc_gtag_ctas = 8;                    // LZ4B200_ENC_GTAG_CTAS: CTAs per SM (tables must stay L2-resident: 16 KiB each)
     DevBuf<uint16_t> d_ttab16;                // K1-T tables
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
@@ -272,14 +276,16 @@ struct lz4b200_ctx {
     // K1-T / K2-T (one block per thread, lz4b200_thread_kernels.cuh): used for batches of at least thread_min_blocks
     // blocks of <= 64 KiB without a dictionary.  LZ4B200_THREAD_MIN / _ENC_THREAD_LANES / _DEC_THREAD_LANES /
     // _ENC_THREADS / _DEC_THREADS override the launch shape (tuning aids).
-    uint32_t enc_thread_min = 4096, dec_thread_min = 4096;
+    uint32_t enc_thread_min = 0xffffffffu, dec_thread_min = 0xffffffffu;   // off by default: measured slower
     int enc_thread_lanes = 0, dec_thread_lanes = 0;   // 0: chosen from the batch size
     uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
     // K1-S (one chain per CTA in shared memory, lz4b200_solo_kernel.cuh): every batch of blocks > 64 KiB, and small
     // batches of small blocks (fewer chains than the GPU has half-SMs).  LZ4B200_ENC_SOLO=0 disables it (A/B aid).
-    int enc_solo = 1, enc_solo_ctas_per_sm = 0;
+    int enc_solo = 0, enc_solo_ctas_per_sm = 0;                                // off by default: measured slower
     uint32_t enc_solo_small_max = 0;          // set from the SM count at context creation
     std::string last_error;
+    uint32_t range_nb = 0;                    // lz4b200_frame_range_compress -> _pack hand-over
+    const uint8_t *range_in = nullptr;
     size_t frame_budget = 256u << 20;         // device bytes the frame decoder's block slots / staged input may take per group
 
     // scratch for host-pointer and frame entry points
@@ -427,6 +433,17 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         // Global-table encoder when the batch has more blocks than the shared-memory-table kernel keeps in flight
         // (24 per SM): 56 slower chains per SM then beat 24 faster ones (17.3 vs 20.1 ms per GiB of 64 KiB blocks);
         // with fewer blocks the shorter chain of the shared-memory tables wins.
+        if (ctx->enc_gtag && ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+            const int m = ctx->enc_gtag / 10;
+            want = (a.nblocks + m - 1) / m;
+            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc_gtag_ctas));
+            const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;             // u32 entries, 8 CTAs x 8 warps max
+            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
+            if (!ctx->check(ctx->d_gtag32.reserve(region * 9u), "gtag")) return LZ4B200_CUDA_ERROR;
+            uint32_t *gt = ctx->d_gtag32.p + slot * region;
+            if (m == 6) lz4_compress_blocks_gtag<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            else lz4_compress_blocks_gtag<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+        } else
         if (ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
             // global-table encoder: 8 warps per CTA, 8 CTAs per SM
             const int m = ctx->enc_gtab / 10, e = ctx->enc_gtab % 10;
@@ -573,7 +590,6 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
                                              (int)kSoloSmemBytes), "solo smem") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo_ctas_per_sm, lz4_compress_blocks_solo, 64,
                                                                       kSoloSmemBytes), "occupancy solo");
-        if (ctx->enc_solo_ctas_per_sm < 1) ctx->enc_solo = 0;
         ctx->enc_solo_small_max = (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm);
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
@@ -593,6 +609,8 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     }
     if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAG")) ctx->enc_gtag = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAG_CTAS")) ctx->enc_gtag_ctas = std::max(1, std::min(8, atoi(g)));
     if (const char *g = getenv("LZ4B200_ENC_GTAB_SMEM")) ctx->enc_gtab_smem = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAB_CARVEOUT")) ctx->enc_gtab_carveout = atoi(g);
     if (getenv("LZ4B200_DEBUG"))
@@ -603,6 +621,7 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
+    if (ctx->enc_solo_ctas_per_sm < 1) ctx->enc_solo = 0;
     if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_THREAD_MIN")) ctx->enc_thread_min = ctx->dec_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_ENC_THREAD_MIN")) ctx->enc_thread_min = (uint32_t)atoll(g);
@@ -631,7 +650,7 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
     ctx->d_off_b.release();
     ctx->d_in_len.release(); ctx->d_out_cap.release(); ctx->d_out_len.release(); ctx->d_info.release();
     ctx->d_seg_size.release(); ctx->d_payload_len.release(); ctx->d_status.release();
-    ctx->d_gtab16.release(); ctx->d_ttab16.release();
+    ctx->d_gtab16.release(); ctx->d_ttab16.release(); ctx->d_gtag32.release();
     delete ctx;
 }
 
@@ -1334,18 +1353,19 @@ size_t lz4b200_frame_bound(size_t n, const lz4b200_frame_info *info)
     return 19 + n + nb * 8 + 8;
 }
 
-lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx, const uint8_t *d_in, size_t in_len,
-                                                    size_t block_size, uint64_t first_block, uint8_t *d_out,
-                                                    size_t out_cap, uint64_t *d_total, uint32_t *d_block_sizes,
-                                                    void *stream)
+// Rank-local half of a (possibly sharded) frame, step 1: compress the blocks of [first_block, ...) into the context's
+// slots, decide compressed-vs-stored per block (frame/compress.rs:301-306) and scan the segment sizes.  *d_total
+// receives the packed size.  Everything stays on the device and on `stream`.
+lz4b200_status lz4b200_frame_range_compress(lz4b200_ctx *ctx, const uint8_t *d_in, size_t in_len, size_t block_size,
+                                            uint64_t first_block, uint64_t *d_total, uint32_t *d_block_sizes, void *stream)
 {
     if (!ctx || !block_size || block_size > (8u << 20)) return LZ4B200_INVALID_ARGUMENT;
     const size_t nblocks = (in_len + block_size - 1) / block_size;
     if (nblocks > 0xffffffffull) return LZ4B200_INVALID_ARGUMENT;
-    if (out_cap < lz4b200_frame_blocks_bound(in_len, block_size)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t nb = (uint32_t)nblocks;
+    ctx->range_nb = nb; ctx->range_in = d_in;
     if (nb == 0) {
         if (d_total) CTX_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, s));
         return LZ4B200_OK;
@@ -1373,13 +1393,80 @@ lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx, const uint
     CTX_CUDA(ctx, cudaGetLastError());
     scan_sizes_kernel<<<1, 1024, 0, s>>>(ctx->d_seg_size.p, ctx->d_seg_off.p, nb);
     CTX_CUDA(ctx, cudaGetLastError());
-    GatherArgs g{ctx->d_slots.p, d_in, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p, ctx->d_payload_len.p,
-                 ctx->d_pick.p, ctx->d_info.p, d_out, ctx->d_seg_off.p, nb};
-    gather_segments_kernel<<<std::min<uint32_t>(nb, (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(g);
-    CTX_CUDA(ctx, cudaGetLastError());
     if (d_total) CTX_CUDA(ctx, cudaMemcpyAsync(d_total, ctx->d_seg_off.p + nb, 8, cudaMemcpyDeviceToDevice, s));
     if (d_block_sizes)
         CTX_CUDA(ctx, cudaMemcpyAsync(d_block_sizes, ctx->d_seg_size.p, nb * 4, cudaMemcpyDeviceToDevice, s));
+    return LZ4B200_OK;
+}
+
+// Step 2: pack the range's [BlockInfo | payload] segments back to back at d_dst + *d_dst_offset.  d_dst may be PEER
+// memory (another GPU's frame buffer mapped over NVLink, lz4b200_peer_open): the pack kernel's stores are then the
+// transfer — the per-rank chunk is never staged in local memory or handed to a separate collective.
+lz4b200_status lz4b200_frame_range_pack(lz4b200_ctx *ctx, uint8_t *d_dst, const uint64_t *d_dst_offset, void *stream)
+{
+    if (!ctx || !d_dst) return LZ4B200_INVALID_ARGUMENT;
+    const uint32_t nb = ctx->range_nb;
+    if (nb == 0) return LZ4B200_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    GatherArgs g{ctx->d_slots.p, ctx->range_in, ctx->d_out_off.p, ctx->d_in_off.p, ctx->d_payload_len.p, ctx->d_payload_len.p,
+                 ctx->d_pick.p, ctx->d_info.p, d_dst, ctx->d_seg_off.p, nb, d_dst_offset};
+    gather_segments_kernel<<<std::min<uint32_t>(std::max<uint32_t>(nb, (uint32_t)ctx->sm_count * 2), (uint32_t)ctx->sm_count * 8),
+                             256, 0, s>>>(g);
+    CTX_CUDA(ctx, cudaGetLastError());
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_frame_compress_blocks_device(lz4b200_ctx *ctx, const uint8_t *d_in, size_t in_len,
+                                                    size_t block_size, uint64_t first_block, uint8_t *d_out,
+                                                    size_t out_cap, uint64_t *d_total, uint32_t *d_block_sizes,
+                                                    void *stream)
+{
+    if (!ctx || !block_size || block_size > (8u << 20)) return LZ4B200_INVALID_ARGUMENT;
+    if (out_cap < lz4b200_frame_blocks_bound(in_len, block_size)) return LZ4B200_COMPRESS_OUTPUT_TOO_SMALL;
+    lz4b200_status st = lz4b200_frame_range_compress(ctx, d_in, in_len, block_size, first_block, d_total, d_block_sizes, stream);
+    if (st != LZ4B200_OK || in_len == 0) return st;
+    return lz4b200_frame_range_pack(ctx, d_out, nullptr, stream);
+}
+
+// ---- peer-mapped buffers (CUDA IPC): rank 0 allocates the frame buffer, the other ranks of the node map it ----------
+lz4b200_status lz4b200_peer_alloc(lz4b200_ctx *ctx, size_t bytes, void **d_ptr, uint8_t *handle64)
+{
+    if (!ctx || !d_ptr || !handle64 || !bytes) return LZ4B200_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    DeviceGuard guard(ctx->device);
+    void *p = nullptr;
+    CTX_CUDA(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    if (!ctx->check(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle")) { cudaFree(p); return LZ4B200_CUDA_ERROR; }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_peer_open(lz4b200_ctx *ctx, const uint8_t *handle64, void **d_ptr)
+{
+    if (!ctx || !d_ptr || !handle64) return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CTX_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_peer_close(lz4b200_ctx *ctx, void *d_ptr)
+{
+    if (!ctx || !d_ptr) return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    CTX_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return LZ4B200_OK;
+}
+
+lz4b200_status lz4b200_peer_free(lz4b200_ctx *ctx, void *d_ptr)
+{
+    if (!ctx || !d_ptr) return LZ4B200_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    CTX_CUDA(ctx, cudaFree(d_ptr));
     return LZ4B200_OK;
 }
 

@@ -261,25 +261,36 @@ __device__ __forceinline__ void tab_fill16(uint4 *at, uint32_t f)
     else *at = make_uint4(f, f, f, f);
 }
 
-template <typename TabT, bool kGT = false>
+// kTag (global u32 tables, blocks <= 64 KiB): an entry is (tag << 16) | position, tag = 16 bits hashed from the 4 bytes
+// at that position.  A probe fetches its candidate's bytes only when the tags agree — a tag mismatch proves the 4-byte
+// comparison of compress.rs:432-438 fails, so the parse is unchanged — which removes ~30 of the 32 speculative sector
+// reads of a batch (the 40 GB of DRAM traffic per GiB that profiles/r1_ncu_summary.json shows for the untagged kernel).
+__device__ __forceinline__ uint32_t tag16(uint32_t v4) { return (v4 * 2246822519u) >> 16; }
+
+template <typename TabT, bool kGT = false, bool kTag = false>
 __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, uint32_t *ring,
                                             bool cont, bool h5, SeqProducer &pr, uint32_t lane)
 {
-    constexpr uint32_t kInvalid = TabTraits<TabT>::kInvalid;
+    static_assert(!kTag || (kGT && sizeof(TabT) == 4), "tagged entries: global u32 tables");
+    constexpr uint32_t kInvalid = kTag ? 0xffffffffu : TabTraits<TabT>::kInvalid;
     const uint32_t lt_mask = (1u << lane) - 1u;
     if (n < 13) {                                               // compress.rs:343-346
         pr.push_final(0, n, lane);
         return;
     }
+    const WordView view(src);
     {
         constexpr uint32_t words = 4096 * sizeof(TabT) / 16;
-        const uint32_t f = cont ? 0xffffffffu : 0u;
+        uint32_t f = cont ? 0xffffffffu : 0u;
+        if (kTag && !cont) {                                    // an empty slot is a candidate at position 0 (compress.rs:353-359):
+            uint32_t lo0, hi0; view.ro5(0, lo0, hi0);           // it must carry position 0's real tag
+            f = tag16(lo0) << 16;
+        }
         uint4 *t128 = reinterpret_cast<uint4 *>(tab);
 #pragma unroll 4
         for (uint32_t i = lane; i < words; i += 32) tab_fill16<kGT>(t128 + i, f);
         __syncwarp();
     }
-    const WordView view(src);
     InputWindow win;
     win.init(src, n, ring);
     const uint32_t last_probe = n - 12;
@@ -289,7 +300,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
     if (!cont) {                                                // compress.rs:353-359
         uint32_t lo, hi; view.ro5(0, lo, hi);
         const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) tab_put<kGT>(tab, s, 0u);
+        if (lane == 0) tab_put<kGT>(tab, s, kTag ? tag16(lo) << 16 : 0u);
         cur = 1;
         __syncwarp();
     }
@@ -317,7 +328,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
                 if (ENC_WINDOW) win.ro5(cur - 2u + win.mis, lo2, hi2); else view.ro5(cur - 2u, lo2, hi2);
                 s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
 #if !ENC_RI_PATCH
-                if (lane == 0) tab_put<kGT>(tab, s2, cur - 2u);
+                if (lane == 0) tab_put<kGT>(tab, s2, kTag ? ((cur - 2u) | (tag16(lo2) << 16)) : cur - 2u);
                 __syncwarp();
                 s2 = 0xffffffffu;
 #endif
@@ -326,6 +337,9 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
             uint32_t cnd = kInvalid;
             if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
+            const uint32_t mytag = kTag ? tag16(v4) : 0u;
+            bool tag_ok = true;
+            if (kTag) { tag_ok = cnd != kInvalid && (cnd >> 16) == mytag; if (cnd != kInvalid) cnd &= 0xffffu; }
 #if ENC_RI_PATCH
             // Nothing waits for the re-insert's table write: a probe on the same slot takes cur-2 directly and the
             // write itself is made with this batch's commits (dropped if a committed probe overwrites the slot).
@@ -337,8 +351,15 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             // speculation was exact.  For w0 <= 3 (89 % of JSON sequences) that is settled with three shuffles;
             // match.any — whose latency grows with the number of distinct keys, ~900 cycles for 32 — only runs
             // for the rest.
-            bool chk = live && cnd != kInvalid && p - cnd <= 65535u;
-            bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+            bool chk = live && cnd != kInvalid && p - cnd <= 65535u && tag_ok;
+            bool hit;
+            if (kTag) {                                         // only lanes whose tag agrees touch memory
+                uint32_t c4 = ~v4;
+                if (chk) c4 = view.ro4(cnd);
+                hit = chk & (c4 == v4);
+            } else {
+                hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+            }
             uint32_t hits = __ballot_sync(kFull, hit);
             const uint32_t terms = (base + 31u * stride > last_probe) ? __ballot_sync(kFull, term) : 0u;   // uniform: only near the block's end
             const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
@@ -356,7 +377,11 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
                 const uint32_t prior = same & lt_mask;
                 const uint32_t le0 = w0 >= 31u ? kFull : ((2u << w0) - 1u);
                 if (__ballot_sync(kFull, prior != 0u) & le0) {
-                    if (prior) {
+                    if (kTag) {                                              // the forwarded candidate is a probe of this batch:
+                        const uint32_t pl = prior ? 31u - __clz(prior) : lane;   // its 4 bytes sit in that lane's register
+                        const uint32_t pv = __shfl_sync(kFull, v4, pl);
+                        if (prior) { cnd = base + pl * stride; hit = pv == v4; }
+                    } else if (prior) {
                         cnd = base + (31u - __clz(prior)) * stride;          // forwarded in-batch write
                         chk = p - cnd <= 65535u;                             // lanes with a prior are never term lanes
                         hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
@@ -374,7 +399,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             const uint32_t upto = win < 32u ? win : width - 1u;
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
-            if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, p);
+            if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, kTag ? (p | (mytag << 16)) : p);
 #if ENC_RI_PATCH
             if (s2 != 0xffffffffu) {                            // uniform: first batch after a match
                 const uint32_t dups = __ballot_sync(kFull, key == s2 && lane <= upto);
@@ -756,10 +781,10 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
 }
 
 // The per-warp block loop of a matcher (shared by the kernels below).
-template <typename TabT, bool kGT>
+template <typename TabT, bool kGT, bool kTag = false>
 __device__ __forceinline__ void matcher_loop(const BatchArgs &a, uint32_t *tickets, TabT *tab, SeqProducer &pr, uint32_t lane)
 {
-    constexpr bool kSmall = sizeof(TabT) == 2;
+    constexpr bool kSmall = sizeof(TabT) == 2 || kTag;
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
         if ((n <= 65536u) != kSmall) continue;
@@ -770,7 +795,7 @@ __device__ __forceinline__ void matcher_loop(const BatchArgs &a, uint32_t *ticke
         }
         const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
         pr.block = b; pr.first = 1;
-        match_block<TabT, kGT>(a.in + a.in_off[b], n, tab, nullptr, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
+        match_block<TabT, kGT, kTag>(a.in + a.in_off[b], n, tab, nullptr, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
     }
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0, lane);
@@ -807,6 +832,32 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
     else
         matcher_loop<TabT, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
+    retire_warp(tickets, gridDim.x * kM);
+}
+
+// Tagged global tables (kTag, see match_block): kM matchers + kE emitters per CTA, 16 KiB of (tag, position) entries per
+// matcher in global memory.  Blocks of at most 65 536 bytes.
+template <int kM, int kE>
+__global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
+lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
+{
+    constexpr int kR = kM / kE;
+    static_assert(kM % kE == 0, "every emitter serves the same number of matchers");
+    __shared__ __align__(16) uint4 q_s[kM * 2 * kSeqBatchEntries];
+    __shared__ uint32_t meta_s[kM * 8];
+    __shared__ __align__(8) uint64_t bars_s[kM * 4];
+    __shared__ EmitState st_s[kM];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x < (uint32_t)kM * 4u) mbar_init(bars_s + threadIdx.x, 1u);
+    __syncthreads();
+    if (warp >= (uint32_t)kM) {
+        const uint32_t e = warp - kM;
+        emit_loop_multi<kR>(a, q_s + e * kR * 2 * kSeqBatchEntries, meta_s + e * kR * 8, bars_s + e * kR * 4,
+                            st_s + e * kR, lane);
+        return;
+    }
+    SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    matcher_loop<uint32_t, true, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
     retire_warp(tickets, gridDim.x * kM);
 }
 

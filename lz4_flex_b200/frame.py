@@ -433,7 +433,7 @@ class FrameDecoder(io.RawIOBase):
                 raise err
             self._hdr, self._flg = hdr, flg
             self._bs = {4: 64 << 10, 5: 256 << 10, 6: 1 << 20, 7: 4 << 20}[(rest[1] >> 4) & 7]
-            self._content_size = int.from_bytes(more[:8], "little") if flg & 0x08 else None
+            self._content_size = int.from_bytes(hdr[6:14], "little") if flg & 0x08 else None
         self._content = _Xxh32(0) if self._flg & 0x04 else None
         self._content_len = 0
         return True

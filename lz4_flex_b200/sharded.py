@@ -3,6 +3,15 @@
 the CPU tests).  Rank r owns the contiguous block range [r*B/G, (r+1)*B/G): block modes depend only on the
 absolute block index, so every rank compresses its range with no communication; the only exchange step is
 the gather of the packed per-rank chunks to rank 0, which prepends the frame header and appends the end mark.
+
+Two implementations of the exchange step:
+  * PeerFrameGather (GPUs of one node, the default on CUDA): rank 0 owns the frame buffer and every rank maps it
+    over NVLink (CUDA IPC).  Per step: an 8-byte-per-rank all_gather of the packed sizes, a device-side prefix sum,
+    and then each rank's PACK KERNEL writes its [BlockInfo | payload] segments straight into rank 0's buffer at its
+    offset — the stores of the pack kernel are the transfer; there is no staging copy, no host synchronisation and no
+    payload collective.  One small all_reduce tells rank 0 that every rank's stores have landed.
+  * gather_frame (any backend; used by the gloo CPU tests and as a fallback): all_gather of sizes + send/recv of the
+    packed chunks.
 """
 from __future__ import annotations
 
@@ -97,3 +106,126 @@ def frame_compress_sharded(local, total_len: int, block_size_id: int, rank: int,
     else:
         part, part_len = compress_range(local, bs, lo)
     return gather_frame(part, part_len, info, rank, world, group)
+
+
+class _DevPtr:
+    """A raw device allocation as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerFrameGather:
+    """The sharded frame encoder of one node with the gather fused into the pack kernel (module docstring).
+
+    Every rank calls step(d_in) with its byte range resident on its GPU; after the step rank 0 holds the frame in
+    `self.frame` (uint8 CUDA tensor view of the shared buffer) and its length in `self.frame_len` (0-d int64 CUDA
+    tensor).  Nothing in step() synchronises with the host."""
+
+    def __init__(self, total_len: int, block_size_id: int, rank: int, world: int, ctx, group=None, base_block: int = 0):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _native
+        self.L = _native.lib()
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.info = FrameInfo(block_size=BlockSize(block_size_id))
+        self.bs = self.info.block_size.get_size()
+        self.total_len = total_len
+        nblocks = -(-total_len // self.bs)
+        self.first_block = base_block + block_range(nblocks, rank, world)[0]   # base_block: the stream continues an earlier one
+        header = self.info.header_bytes()
+        self.header_len = len(header)
+        cap = self.header_len + 4
+        for r in range(world):
+            lo, hi = byte_range(total_len, self.bs, r, world)
+            cap += self.L.lz4b200_frame_blocks_bound(hi - lo, self.bs)
+        self.cap = cap
+        dev = torch.device("cuda", ctx.device)
+        self.dev = dev
+        handle = (C.c_uint8 * 64)()
+        p = C.c_void_p()
+        self._owned = self._mapped = None
+        if rank == 0:
+            st = self.L.lz4b200_peer_alloc(ctx.handle, cap, C.byref(p), handle)
+            if st != 0:
+                raise RuntimeError("lz4b200_peer_alloc failed: " + ctx.last_cuda_error())
+            self._owned = p.value
+        if world > 1:
+            box = [bytes(handle) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0, group=group)
+            if rank != 0:
+                h = (C.c_uint8 * 64).from_buffer_copy(box[0])
+                st = self.L.lz4b200_peer_open(ctx.handle, h, C.byref(p))
+                if st != 0:
+                    raise RuntimeError("lz4b200_peer_open failed: " + ctx.last_cuda_error())
+                self._mapped = p.value
+        self.frame_ptr = p.value
+        self.d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_all = torch.zeros(world, dtype=torch.int64, device=dev)
+        self.d_off = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.frame_len = torch.zeros((), dtype=torch.int64, device=dev)
+        self.frame = None
+        if rank == 0:
+            self.frame = torch.as_tensor(_DevPtr(self.frame_ptr, cap), device=dev)
+            self.frame[: self.header_len] = torch.frombuffer(bytearray(header), dtype=torch.uint8).to(dev)
+            self._four = torch.arange(4, device=dev)
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(self, d_in, timed: bool = False):
+        import torch
+        import torch.distributed as dist
+        s = torch.cuda.current_stream().cuda_stream
+        n = d_in.numel()
+        if timed:
+            self.ev[0].record()
+        st = self.L.lz4b200_frame_range_compress(self.ctx.handle, d_in.data_ptr() if n else None, n, self.bs, self.first_block,
+                                                 self.d_total.data_ptr(), None, s)
+        if st != 0:
+            from .errors import error_from_status
+            raise error_from_status(st, detail=self.ctx.last_cuda_error())
+        if timed:
+            self.ev[1].record()
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.d_all, self.d_total, group=self.group)
+        else:
+            self.d_all.copy_(self.d_total)
+        ends = torch.cumsum(self.d_all, 0)
+        self.d_off.copy_((ends[self.rank] - self.d_all[self.rank] + self.header_len).reshape(1))
+        st = self.L.lz4b200_frame_range_pack(self.ctx.handle, self.frame_ptr, self.d_off.data_ptr(), s)
+        if st != 0:
+            from .errors import error_from_status
+            raise error_from_status(st, detail=self.ctx.last_cuda_error())
+        if self.world > 1:
+            dist.all_reduce(self.d_flag, group=self.group)          # every rank's pack kernel has completed
+        if self.rank == 0:
+            end = ends[-1] + self.header_len
+            self.frame[end + self._four] = 0                        # EndMark
+            self.frame_len = end + 4
+        if timed:
+            self.ev[2].record()
+
+    def timings_ms(self):
+        """(compress kernel ms, exchange + pack ms) of the last timed step (after a synchronize)."""
+        return self.ev[0].elapsed_time(self.ev[1]), self.ev[1].elapsed_time(self.ev[2])
+
+    def result(self):
+        """Rank 0: the frame bytes as a CUDA tensor slice (synchronises to read the length)."""
+        if self.rank != 0:
+            return None
+        return self.frame[: int(self.frame_len.item())]
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self._mapped:
+            self.L.lz4b200_peer_close(self.ctx.handle, self._mapped)
+            self._mapped = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)                          # nobody still maps the buffer
+        if self._owned:
+            self.frame = None
+            self.L.lz4b200_peer_free(self.ctx.handle, self._owned)
+            self._owned = None

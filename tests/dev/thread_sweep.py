@@ -61,12 +61,14 @@ def run(env, label, iters=5):
     print(f"{label:44s} compress {min(cms[1:]):8.3f} ms  decompress {min(dms[1:]):8.3f} ms  parity c={ok_c} d={ok_d}", flush=True)
     ctx.close()
 
-run({"LZ4B200_THREAD_MIN": "4000000000"}, "round-1 warp kernels (gtab / G=8)")
-for lanes in (32, 16, 8, 4):
-    if lanes == 4:
-        continue
-    run({"LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
-for thr in (8192, 4096):
-    run({"LZ4B200_ENC_THREAD_LANES": "16", "LZ4B200_DEC_THREAD_LANES": "16", "LZ4B200_ENC_THREADS": str(thr), "LZ4B200_DEC_THREADS": str(thr)},
-        f"thread kernels, 16 lanes, {thr} threads")
-run({}, "default")
+MODE = sys.argv[3] if len(sys.argv) > 3 else "gtag"
+if MODE == "thread":
+    run({"LZ4B200_THREAD_MIN": "4000000000"}, "round-1 warp kernels (gtab / G=8)")
+    for lanes in (32, 16, 8):
+        run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
+else:
+    run({"LZ4B200_ENC_GTAG": "0"}, "untagged gtab 7+1 x8 (round 1)")
+    for ctas in (8, 7, 6, 5):
+        run({"LZ4B200_ENC_GTAG_CTAS": str(ctas)}, f"tagged tables 7+1, {ctas} CTAs/SM")
+    run({"LZ4B200_ENC_GTAG": "62"}, "tagged tables 6+2, 8 CTAs/SM")
+    run({}, "default")

@@ -2,7 +2,8 @@
 environment switches (a fresh context reads them at creation):
   K1-T / K2-T  one block per thread          (lz4b200_thread_kernels.cuh)   LZ4B200_THREAD_MIN=1
   K1-S         one chain per CTA, smem ring  (lz4b200_solo_kernel.cuh)      LZ4B200_ENC_SOLO_SMALL_MAX=1000000
-  warp kernels matcher/emitter warps, lane groups (round 1)                 LZ4B200_THREAD_MIN=4e9, LZ4B200_ENC_SOLO=0
+  warp kernels matcher/emitter warps, lane groups (default)                 LZ4B200_THREAD_MIN=4e9, LZ4B200_ENC_SOLO=0
+               (global tables tagged by default; LZ4B200_ENC_GTAG=0: untagged)
 Bit-exact compressed bytes in all three parse modes, exact round trips, identical error codes / expected fields."""
 import os
 
@@ -19,8 +20,9 @@ VARIANTS = {
     "thread": {"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_SOLO": "0"},
     "thread8": {"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_SOLO": "0", "LZ4B200_ENC_THREAD_LANES": "8", "LZ4B200_DEC_THREAD_LANES": "8"},
     "thread_few": {"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_SOLO": "0", "LZ4B200_ENC_THREADS": "64", "LZ4B200_DEC_THREADS": "64"},
-    "solo": {"LZ4B200_ENC_SOLO_SMALL_MAX": "1000000", "LZ4B200_THREAD_MIN": "4000000000"},
+    "solo": {"LZ4B200_ENC_SOLO": "1", "LZ4B200_ENC_SOLO_SMALL_MAX": "1000000", "LZ4B200_THREAD_MIN": "4000000000"},
     "warp": {"LZ4B200_THREAD_MIN": "4000000000", "LZ4B200_ENC_SOLO": "0"},
+    "warp_untagged": {"LZ4B200_ENC_GTAG": "0"},
 }
 
 
@@ -75,7 +77,7 @@ def test_big_blocks_and_unaligned(vctx):
     outs, st, _ = block.decompress_blocks(comp, [len(x) for x in cases], vctx)
     assert outs == cases
     # unaligned sub-buffers: every input / output misalignment mod 8 through the batch descriptors
-    src = np.frombuffer(corpus.load("compression_66k_JSON.txt"), dtype=np.uint8)
+    src = corpus.tiled("compression_66k_JSON.txt", 100000)
     lens = np.array([9000 + 7 * k for k in range(64)], dtype=np.uint32)
     offs = np.array([k * 1001 + (k % 8) + 8 * (k % 3) for k in range(64)], dtype=np.uint64)
     out, ooff, olen = block.compress_batch(src, offs, lens, ctx=vctx)
@@ -83,6 +85,7 @@ def test_big_blocks_and_unaligned(vctx):
         want = oracle.compress_block(src[int(offs[k]): int(offs[k]) + int(lens[k])].tobytes())
         assert out[int(ooff[k]): int(ooff[k]) + int(olen[k])].tobytes() == want, k
     back = np.zeros(int(lens.sum()) + 64 * 8, dtype=np.uint8)
+    assert int(offs[-1]) + int(lens[-1]) <= src.size
     boff = np.cumsum(np.concatenate([[0], lens[:-1].astype(np.uint64) + np.arange(1, 64, dtype=np.uint64) % 8])).astype(np.uint64)
     ol, st, _ = block.decompress_batch(out, ooff, olen, back, boff, lens, ctx=vctx)
     assert not st.any()
@@ -146,3 +149,38 @@ def _ext(v):
         b.append(255); v -= 255
     b.append(v)
     return bytes(b)
+
+
+def test_many_blocks_global_table_kernels(vctx):
+    """More blocks than the shared-memory-table kernel keeps in flight (24 per SM): the launcher's global-table kernel
+    (tagged entries by default) — ragged block lengths, all three parse modes, every block compared with the oracle."""
+    src = corpus.tiled("compression_66k_JSON.txt", 40 << 20)
+    d = np.frombuffer(corpus.load("dickens.txt"), dtype=np.uint8)
+    src[20 << 20: 30 << 20] = d[: 10 << 20]
+    rng = np.random.default_rng(77)
+    lens = rng.integers(1500, 12000, 6000).astype(np.uint32)
+    lens[:64] = np.arange(64, dtype=np.uint32)
+    lens[64:80] = 65536
+    offs = np.zeros(lens.size, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+    assert int(offs[-1]) + int(lens[-1]) <= src.size
+    nb = lens.size
+    slot = 72112
+    soff = np.arange(nb, dtype=np.uint64) * slot
+    scap = np.full(nb, slot, dtype=np.uint32)
+    for fl, tabfn in ((0, None), (block.BLOCK_HASH5_ALWAYS, oracle.compress_block_fresh_h5),
+                      (block.BLOCK_HASH5_ALWAYS | block.BLOCK_CONT, oracle.compress_block_cont)):
+        out, ooff, olen = block.compress_batch(src, offs, lens, None if fl == 0 else np.full(nb, fl, dtype=np.uint8), ctx=vctx)
+        if tabfn is None:
+            want = np.zeros(nb * slot, dtype=np.uint8)
+            wlen, wst = oracle.compress_batch(src, offs, lens, want, soff, scap, os.cpu_count())
+            assert np.array_equal(wlen, olen)
+            packed = np.concatenate([want[b * slot: b * slot + int(wlen[b])] for b in range(nb)])
+            assert np.array_equal(out[: packed.size], packed)
+        else:
+            for b in list(range(0, 90)) + list(range(90, nb, 61)):
+                a, n = int(offs[b]), int(lens[b])
+                assert out[int(ooff[b]): int(ooff[b]) + int(olen[b])].tobytes() == tabfn(src[a:a + n].tobytes()), (fl, b)
+    back = np.zeros(int(offs[-1]) + int(lens[-1]), dtype=np.uint8)
+    ol, st, _ = block.decompress_batch(out, ooff, olen, back, offs, lens, ctx=vctx)
+    assert not st.any() and np.array_equal(back, src[: back.size])
