@@ -263,7 +263,9 @@ struct lz4b200_ctx {
     bool enc_gtab_carveout_set = false;
     DevBuf<uint16_t> d_gtab16;
     DevBuf<uint32_t> d_gtag32;                // tagged global tables (lz4_compress_blocks_gtag)
-    int enc_gtag = 71;                        // LZ4B200_ENC_GTAG=10*matchers+emitters (71|62), 0: untagged gtab kernel
+    int enc_g16 = 0;                          // LZ4B200_ENC_G16=10*matcher warps+emitters (62|71): half-warp matchers, 0: off
+    int enc_g16_ctas = 8;                     // LZ4B200_ENC_G16_CTAS
+    int enc_gtag = 0;                         // LZ4B200_ENC_GTAG=10*matchers+emitters (71|62): tagged entries (measured slower: 19.4 vs 17.8 ms), 0: off
     int enc_gtag_ctas = 8;                    // LZ4B200_ENC_GTAG_CTAS: CTAs per SM (tables must stay L2-resident: 16 KiB each)
     DevBuf<uint16_t> d_ttab16;                // K1-T tables
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
@@ -281,6 +283,7 @@ struct lz4b200_ctx {
     uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
     // K1-S (one chain per CTA in shared memory, lz4b200_solo_kernel.cuh): every batch of blocks > 64 KiB, and small
     // batches of small blocks (fewer chains than the GPU has half-SMs).  LZ4B200_ENC_SOLO=0 disables it (A/B aid).
+    int enc_solo2_ctas_per_sm = 0;
     int enc_solo = 0, enc_solo_ctas_per_sm = 0;                                // off by default: measured slower
     uint32_t enc_solo_small_max = 0;          // set from the SM count at context creation
     std::string last_error;
@@ -400,6 +403,12 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     if (!a.dict_len && ctx->enc_solo && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
+        if (ctx->enc_solo == 2) {                         // warp matcher over the ring (K1-S2)
+            const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo2_ctas_per_sm));
+            lz4_compress_blocks_solo2<<<grid, 64, kSolo2SmemBytes, s>>>(a, tickets + 4);
+            CTX_CUDA(ctx, cudaGetLastError());
+            return LZ4B200_OK;
+        }
         const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm));
         lz4_compress_blocks_solo<<<grid, 64, kSoloSmemBytes, s>>>(a, tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
@@ -433,6 +442,17 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         // Global-table encoder when the batch has more blocks than the shared-memory-table kernel keeps in flight
         // (24 per SM): 56 slower chains per SM then beat 24 faster ones (17.3 vs 20.1 ms per GiB of 64 KiB blocks);
         // with fewer blocks the shorter chain of the shared-memory tables wins.
+        if (ctx->enc_g16 && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+            const int m = ctx->enc_g16 / 10;                                          // matcher warps per CTA, 2 chains each
+            want = (a.nblocks + 2 * m - 1) / (2 * m);
+            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
+            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries, 8 CTAs x 16 chains max
+            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
+            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab16")) return LZ4B200_CUDA_ERROR;
+            uint16_t *gt = ctx->d_gtab16.p + slot * region;
+            if (m == 7) lz4_compress_blocks_gtab16<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            else lz4_compress_blocks_gtab16<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+        } else
         if (ctx->enc_gtag && ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
             const int m = ctx->enc_gtag / 10;
             want = (a.nblocks + m - 1) / m;
@@ -451,7 +471,7 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * (m == 15 ? 4u : 8u));
             // one table region per concurrently running launch (the host pipeline launches from up to 8 lanes):
             // the ticket block doubles as the region selector
-            const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;             // u16 entries
+            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries (sized for the half-warp kernel too)
             const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + slot * region;
@@ -590,6 +610,10 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
                                              (int)kSoloSmemBytes), "solo smem") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo_ctas_per_sm, lz4_compress_blocks_solo, 64,
                                                                       kSoloSmemBytes), "occupancy solo");
+        ok = ok && ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kSolo2SmemBytes), "solo2 smem") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo2_ctas_per_sm, lz4_compress_blocks_solo2, 64,
+                                                                      kSolo2SmemBytes), "occupancy solo2");
         ctx->enc_solo_small_max = (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm);
     }
     if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
@@ -609,6 +633,22 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     }
     if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
+    // The global-table encoders mark their table accesses L2::evict_last; how much of the L2 such lines may occupy is the
+    // device's persisting-L2 limit (0 by default: the hint is then ignored).
+    {
+        int maxp = 0;
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
+        long want_mb = -1;
+        if (const char *g = getenv("LZ4B200_L2_PERSIST_MB")) want_mb = atol(g);
+        if (want_mb >= 0) {
+            size_t bytes = std::min<size_t>((size_t)want_mb << 20, (size_t)maxp);
+            cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+            if (getenv("LZ4B200_DEBUG"))
+                fprintf(stderr, "lz4b200: persisting L2 limit %zu of max %d bytes: %s\n", bytes, maxp, cudaGetErrorString(e));
+        }
+    }
+    if (const char *g = getenv("LZ4B200_ENC_G16")) ctx->enc_g16 = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_G16_CTAS")) ctx->enc_g16_ctas = std::max(1, std::min(8, atoi(g)));
     if (const char *g = getenv("LZ4B200_ENC_GTAG")) ctx->enc_gtag = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAG_CTAS")) ctx->enc_gtag_ctas = std::max(1, std::min(8, atoi(g)));
     if (const char *g = getenv("LZ4B200_ENC_GTAB_SMEM")) ctx->enc_gtab_smem = atoi(g);
@@ -621,7 +661,7 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
-    if (ctx->enc_solo_ctas_per_sm < 1) ctx->enc_solo = 0;
+    if (ctx->enc_solo_ctas_per_sm < 1 || ctx->enc_solo2_ctas_per_sm < 1) ctx->enc_solo = 0;
     if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_THREAD_MIN")) ctx->enc_thread_min = ctx->dec_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_ENC_THREAD_MIN")) ctx->enc_thread_min = (uint32_t)atoll(g);

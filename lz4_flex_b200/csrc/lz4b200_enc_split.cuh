@@ -267,9 +267,9 @@ __device__ __forceinline__ void tab_fill16(uint4 *at, uint32_t f)
 // reads of a batch (the 40 GB of DRAM traffic per GiB that profiles/r1_ncu_summary.json shows for the untagged kernel).
 __device__ __forceinline__ uint32_t tag16(uint32_t v4) { return (v4 * 2246822519u) >> 16; }
 
-template <typename TabT, bool kGT = false, bool kTag = false>
-__device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, uint32_t *ring,
-                                            bool cont, bool h5, SeqProducer &pr, uint32_t lane)
+template <typename TabT, bool kGT = false, bool kTag = false, typename View = WordView>
+__device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *tab, uint32_t *ring,
+                                                 bool cont, bool h5, SeqProducer &pr, uint32_t lane)
 {
     static_assert(!kTag || (kGT && sizeof(TabT) == 4), "tagged entries: global u32 tables");
     constexpr uint32_t kInvalid = kTag ? 0xffffffffu : TabTraits<TabT>::kInvalid;
@@ -278,7 +278,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         pr.push_final(0, n, lane);
         return;
     }
-    const WordView view(src);
+    view.advance(0u);
     {
         constexpr uint32_t words = 4096 * sizeof(TabT) / 16;
         uint32_t f = cont ? 0xffffffffu : 0u;
@@ -292,7 +292,9 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         __syncwarp();
     }
     InputWindow win;
-    win.init(src, n, ring);
+#if ENC_WINDOW
+    win.init(reinterpret_cast<const uint8_t *>(view.w) + view.mis, n, ring);
+#endif
     const uint32_t last_probe = n - 12;
     const uint32_t lim = n - 6;                                 // matches end before the last END_OFFSET bytes
     uint32_t anchor = 0, cur = 0;
@@ -314,6 +316,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         uint32_t base = cur, stride = 1, width = ENC_FIRST_WIDTH, cand, mpos;
         bool in_win = ENC_WINDOW != 0;                          // first batch: probe bytes come from the ring
         for (;;) {                                              // probe batches: compress.rs:373-439
+            view.advance(base);
             const uint32_t p = base + lane * stride;
             const bool act = lane < width;
             const bool term = act && p > last_probe;
@@ -427,12 +430,12 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         const uint32_t room = min(cand, mpos - anchor);         // how far both sides may step back (0 for literal-free sequences)
         const uint32_t qf = mpos + 4u + lane;
         const bool inf = qf < lim;
-        const uint8_t f1 = in_win ? win.byte(qf + win.mis) : __ldg(src + (inf ? qf : mpos));
-        const uint8_t f2 = __ldg(src + (inf ? qf : mpos) - dist);
+        const uint8_t f1 = in_win ? win.byte(qf + win.mis) : view.byte(inf ? qf : mpos);
+        const uint8_t f2 = view.byte((inf ? qf : mpos) - dist);
         uint32_t kb = 0;
         if (room) {                                             // compress.rs:272-287
             const bool inb = lane < room;
-            const uint8_t b1 = __ldg(src + mpos - (inb ? 1u + lane : 0u)), b2 = __ldg(src + cand - (inb ? 1u + lane : 0u));
+            const uint8_t b1 = view.byte(mpos - (inb ? 1u + lane : 0u)), b2 = view.byte(cand - (inb ? 1u + lane : 0u));
             const uint32_t bad = ~__ballot_sync(kFull, inb && b1 == b2);
             kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
         }
@@ -444,7 +447,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             while (kb == 32u) {                                 // more than 32 bytes backwards: rare
                 const uint32_t room2 = min(cand, mpos - anchor);
                 const bool inb = lane < room2;
-                const uint8_t b1 = __ldg(src + mpos - (inb ? 1u + lane : 0u)), b2 = __ldg(src + cand - (inb ? 1u + lane : 0u));
+                const uint8_t b1 = view.byte(mpos - (inb ? 1u + lane : 0u)), b2 = view.byte(cand - (inb ? 1u + lane : 0u));
                 const uint32_t bad = ~__ballot_sync(kFull, inb && b1 == b2);
                 kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
                 mpos -= kb; cand -= kb;
@@ -452,6 +455,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         }
         if (kf == 32u) {                                        // long match: 128 bytes per round (compress.rs:156-216)
             for (;;) {
+                view.advance(end);
                 const uint32_t pos = end + 4u * lane;
                 const bool full = pos + 4u <= lim;              // this lane's word lies before n - END_OFFSET
                 const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
@@ -466,7 +470,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
             }
             if (end < lim) {                                    // a word that crossed n - 6: at most 3 more bytes
                 const uint32_t q = end + lane;
-                const bool ok = lane < 4u && q < lim && __ldg(src + (q < lim ? q : end)) == __ldg(src + (q < lim ? q : end) - dist);
+                const bool ok = lane < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
                 end += (uint32_t)__ffs(~__ballot_sync(kFull, ok)) - 1u;
             }
         }
@@ -474,6 +478,14 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
         anchor = cur = end;
         ri = true;
     }
+}
+
+template <typename TabT, bool kGT = false, bool kTag = false>
+__device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uint32_t n, TabT *tab, uint32_t *ring,
+                                            bool cont, bool h5, SeqProducer &pr, uint32_t lane)
+{
+    WordView view(src);
+    match_block_view<TabT, kGT, kTag>(view, n, tab, ring, cont, h5, pr, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -859,6 +871,255 @@ lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
     matcher_loop<uint32_t, true, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
     retire_warp(tickets, gridDim.x * kM);
+}
+
+// =============================================================================================
+// Half-warp matchers (lz4_compress_blocks_gtab16): TWO chains per matcher warp, 16 lanes each.
+// The global-table kernel is bound by instruction issue (13.8 G warp-instructions per GiB at IPC 2.6 of 4 per SM,
+// profiles/r1_ncu_summary.json), not by HBM: a sequence costs ~230 matcher instructions whether its batch needed 1 probe
+// or 32.  Here the same instruction stream serves two blocks at once: each half of a warp owns a block, a table and a
+// tuple ring, every warp-level primitive runs under the half's mask, and the halves stay in step because the compiler
+// reconverges them at the end of every loop (a half that found its match waits while the other finishes its extra
+// batch).  A batch is 16 probes (P(hit within 16) = 97 % on JSON, parse statistics in DESIGN.md), so the step rule of
+// compress.rs:374-378 (32 probes per stride value) takes two batches per stride.
+// =============================================================================================
+struct HalfWarp {
+    uint32_t sub, gshift, gmask;
+    __device__ __forceinline__ explicit HalfWarp(uint32_t lane) : sub(lane & 15u), gshift(lane & 16u), gmask(0xffffu << (lane & 16u)) {}
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & 0xffffu; }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(gmask, v, (int)src, 16); }
+    __device__ __forceinline__ uint32_t match_any(uint32_t key) const { return (__match_any_sync(gmask, key) >> gshift) & 0xffffu; }
+    __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
+};
+
+struct SeqProducerG {                            // SeqProducer for a lane group (all state uniform within the group)
+    uint4 *q;
+    volatile uint32_t *meta;
+    uint64_t *bars;
+    uint32_t k, qn, block, first;
+    HalfWarp g;
+    __device__ __forceinline__ void flush(uint32_t last)
+    {
+        const uint32_t h = k & 1u;
+        if (g.sub == 0) {
+            meta[h * 4 + 0] = block;
+            meta[h * 4 + 1] = qn;
+            meta[h * 4 + 2] = first | (last << 1);
+            mbar_arrive(bars + h);
+        }
+        k++; qn = 0; first = 0;
+        if (k >= 2) mbar_wait(bars + 2 + (k & 1u), ((k >> 1) - 1u) & 1u);
+        g.sync();
+    }
+    __device__ __forceinline__ void push(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end)
+    {
+        if (g.sub == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, mpos, dist, end);
+        qn++;
+        if (qn == kSeqBatchEntries) flush(0);
+    }
+    __device__ __forceinline__ void push_final(uint32_t anchor, uint32_t n)
+    {
+        if (g.sub == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, 0u, 0u, n);
+        qn++;
+        flush(1);
+    }
+};
+
+// The search half of compress_internal (compress.rs:318-489) for one block on 16 lanes; u16 table in global memory.
+// Same scheme as match_block_view (speculative pre-batch candidates, shuffles / match.any for in-batch slot collisions,
+// commit of the executed probes), 16 probes per batch, 16 bytes per extension round.
+__device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src, uint32_t n, uint16_t *tab, bool cont, bool h5,
+                                                 SeqProducerG &pr, const HalfWarp &g)
+{
+    constexpr uint32_t G = 16u, kInvalid = 0xffffu, kAll = 0xffffu;
+    const uint32_t sub = g.sub, lt_mask = (1u << sub) - 1u;
+    if (n < 13) {                                               // compress.rs:343-346
+        pr.push_final(0, n);
+        return;
+    }
+    const WordView view(src);
+    {
+        const uint32_t f = cont ? 0xffffffffu : 0u;
+        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
+#pragma unroll 4
+        for (uint32_t i = sub; i < 512u; i += G) tab_fill16<true>(t128 + i, f);
+        g.sync();
+    }
+    const uint32_t last_probe = n - 12, lim = n - 6;
+    uint32_t anchor = 0, cur = 0;
+    bool ri = false;                                            // T[H(cur-2)] = cur-2 still owed (compress.rs:460-461)
+    if (!cont) {                                                // compress.rs:353-359
+        uint32_t lo, hi; view.ro5(0, lo, hi);
+        const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
+        if (sub == 0) tab_put<true>(tab, s, 0u);
+        cur = 1;
+        g.sync();
+    }
+    for (;;) {                                                  // one sequence per iteration
+        uint32_t base = cur, nbatch = 0, cand, mpos;
+        for (;;) {                                              // probe batches: compress.rs:373-439
+            const uint32_t stride = (nbatch >> 1) + 1u;         // 32 probes per step value = two batches of 16
+            const uint32_t p = base + sub * stride;
+            const bool term = p > last_probe, live = !term;
+            uint32_t v4, hi;
+            view.ro5(live ? p : 0u, v4, hi);
+            if (ri) {
+                uint32_t lo2, hi2; view.ro5(cur - 2u, lo2, hi2);
+                const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+                if (sub == 0) tab_put<true>(tab, s2, cur - 2u);
+                g.sync();
+                ri = false;
+            }
+            uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
+            uint32_t cnd = kInvalid;
+            if (live) cnd = tab_get<true>(tab, key); else key = 0x10000u | sub;
+            bool chk = live && cnd != kInvalid && p - cnd <= 65535u;
+            bool hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+            uint32_t hits = g.ballot(hit);
+            const uint32_t terms = (base + (G - 1u) * stride > last_probe) ? g.ballot(term) : 0u;
+            const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : G;
+            uint32_t same = 1u << sub;                          // lanes of this batch on my slot (incl. me)
+            bool exact = w0 == 0u;
+            if (w0 >= 1u && w0 <= 3u) {
+                const uint32_t k0 = g.shfl(key, 0), k1 = g.shfl(key, 1), k2 = g.shfl(key, 2);
+                const bool clash = (sub >= 1u && key == k0) || (sub >= 2u && key == k1) || (sub >= 3u && key == k2);
+                exact = g.ballot(clash && sub <= w0) == 0u;
+            }
+            if (!exact) {
+                same = g.match_any(key);
+                const uint32_t prior = same & lt_mask;
+                const uint32_t le0 = w0 >= G - 1u ? kAll : ((2u << w0) - 1u);
+                if (g.ballot(prior != 0u) & le0) {
+                    if (prior) {
+                        cnd = base + (31u - __clz(prior)) * stride;          // forwarded in-batch write
+                        chk = p - cnd <= 65535u;                             // lanes with a prior are never term lanes
+                        hit = chk & (view.ro4(chk ? cnd : 0u) == v4);
+                    }
+                    hits = g.ballot(hit);
+                }
+            }
+            const uint32_t win = hits ? (uint32_t)__ffs(hits) - 1u : G;
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : G;
+            if (tfirst < win) {                                 // compress.rs:381-384: the rest is literals
+                pr.push_final(anchor, n);
+                return;
+            }
+            // commit the table writes of probes 0..win (last writer per slot wins)
+            const uint32_t upto = win < G ? win : G - 1u;
+            const uint32_t mine = same & ((2u << upto) - 1u);
+            if (sub <= upto && (31u - __clz(mine)) == sub) tab_put<true>(tab, key, p);
+            g.sync();
+            if (win < G) {
+                mpos = base + win * stride;
+                cand = g.shfl(cnd, win);
+                break;
+            }
+            base += G * stride;
+            nbatch++;
+        }
+        const uint32_t dist = mpos - cand;
+        // ---- extension: the first forward round (16 bytes) and the backward round share one memory round trip
+        const uint32_t room = min(cand, mpos - anchor);
+        const uint32_t qf = mpos + 4u + sub;
+        const bool inf = qf < lim;
+        const uint8_t f1 = view.byte(inf ? qf : mpos), f2 = view.byte((inf ? qf : mpos) - dist);
+        uint32_t kb = 0;
+        if (room) {                                             // compress.rs:272-287
+            const bool inb = sub < room;
+            const uint8_t b1 = view.byte(mpos - (inb ? 1u + sub : 0u)), b2 = view.byte(cand - (inb ? 1u + sub : 0u));
+            const uint32_t bad = ~g.ballot(inb && b1 == b2) & kAll;
+            kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
+        }
+        const uint32_t badf = ~g.ballot(inf && f1 == f2) & kAll;
+        const uint32_t kf = badf ? (uint32_t)__ffs(badf) - 1u : G;
+        uint32_t end = mpos + 4u + kf;
+        if (kb) {
+            mpos -= kb; cand -= kb;
+            while (kb == G) {                                   // more than 16 bytes backwards: rare
+                const uint32_t room2 = min(cand, mpos - anchor);
+                const bool inb = sub < room2;
+                const uint8_t b1 = view.byte(mpos - (inb ? 1u + sub : 0u)), b2 = view.byte(cand - (inb ? 1u + sub : 0u));
+                const uint32_t bad = ~g.ballot(inb && b1 == b2) & kAll;
+                kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
+                mpos -= kb; cand -= kb;
+            }
+        }
+        if (kf == G) {                                          // long match: 64 bytes per round (compress.rs:156-216)
+            for (;;) {
+                const uint32_t pos = end + 4u * sub;
+                const bool full = pos + 4u <= lim;              // this lane's word lies before n - END_OFFSET
+                const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
+                const uint32_t nm = full ? (x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u) : 0u;
+                const uint32_t bad = g.ballot(nm < 4u);
+                if (bad) {
+                    const uint32_t fl = (uint32_t)__ffs(bad) - 1u;
+                    end += 4u * fl + g.shfl(nm, fl);
+                    break;
+                }
+                end += 4u * G;
+            }
+            if (end < lim) {                                    // a word that crossed n - 6: at most 3 more bytes
+                const uint32_t q = end + sub;
+                const bool ok = sub < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
+                end += (uint32_t)__ffs(~g.ballot(ok) & kAll) - 1u;
+            }
+        }
+        pr.push(anchor, mpos, dist, end);
+        anchor = cur = end;
+        ri = true;
+    }
+}
+
+// kM matcher warps (2 chains each) + kE emitter warps per CTA; 8 KiB u16 table per chain in global memory.
+template <int kM, int kE>
+__global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
+lz4_compress_blocks_gtab16(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
+{
+    constexpr int kC = 2 * kM, kR = kC / kE;                   // chains per CTA, rings per emitter
+    static_assert(kC % kE == 0, "every emitter serves the same number of chains");
+    __shared__ __align__(16) uint4 q_s[kC * 2 * kSeqBatchEntries];
+    __shared__ uint32_t meta_s[kC * 8];
+    __shared__ __align__(8) uint64_t bars_s[kC * 4];
+    __shared__ EmitState st_s[kC];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x < (uint32_t)kC * 4u) mbar_init(bars_s + threadIdx.x, 1u);
+    __syncthreads();
+    if (warp >= (uint32_t)kM) {
+        const uint32_t e = warp - kM;
+        emit_loop_multi<kR>(a, q_s + e * kR * 2 * kSeqBatchEntries, meta_s + e * kR * 8, bars_s + e * kR * 4,
+                            st_s + e * kR, lane);
+        return;
+    }
+    const HalfWarp g(lane);
+    const uint32_t chain = warp * 2u + (lane >> 4);
+    SeqProducerG pr{q_s + chain * 2 * kSeqBatchEntries, meta_s + chain * 8, bars_s + chain * 4, 0u, 0u, 0u, 0u, g};
+    uint16_t *tab = gtab + ((size_t)blockIdx.x * kC + chain) * 4096;
+    for (;;) {
+        uint32_t b = 0;
+        if (g.sub == 0) b = atomicAdd(&tickets[0], 1u);
+        b = g.shfl(b, 0);
+        if (b >= a.nblocks) break;
+        const uint32_t n = a.in_len[b];
+        if (n > 65536u) continue;                               // blocks above 64 KiB belong to the u32-table kernel
+        const uint32_t fl = a.flags ? a.flags[b] : 0u;
+        if ((uint64_t)a.out_cap[b] < max_output_size_dev(n)) {              // compress.rs:338-340
+            if (g.sub == 0) { a.out_len[b] = 0; a.status[b] = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; }
+            continue;
+        }
+        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
+        pr.block = b; pr.first = 1;
+        match_block_half(a.in + a.in_off[b], n, tab, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, g);
+    }
+    pr.block = kExitBlock; pr.first = 0;
+    pr.flush(0);
+    if (g.sub == 0) {
+        __threadfence();
+        if (atomicAdd(&tickets[1], 1u) == gridDim.x * kC - 1u) {
+            tickets[0] = 0;
+            tickets[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 template <typename TabT, int kPairs>

@@ -128,6 +128,9 @@ struct WordView {
         lo = __funnelshift_r(a, b, sh);
         hi = (b >> sh) & 0xffu;
     }
+    __device__ __forceinline__ uint8_t byte(uint32_t pos) const { return __ldg(reinterpret_cast<const uint8_t *>(w) + mis + pos); }
+    // the matcher announces the start of a probe batch / sequence here (a view that stages data reacts; this one reads global memory directly)
+    __device__ __forceinline__ void advance(uint32_t) const {}
 };
 
 // =============================================================================================

@@ -1,9 +1,9 @@
 """Every K1 / K2 kernel family against the oracle on the same ragged batch, each forced through the launcher's
 environment switches (a fresh context reads them at creation):
   K1-T / K2-T  one block per thread          (lz4b200_thread_kernels.cuh)   LZ4B200_THREAD_MIN=1
-  K1-S         one chain per CTA, smem ring  (lz4b200_solo_kernel.cuh)      LZ4B200_ENC_SOLO_SMALL_MAX=1000000
+  K1-S / K1-S2 one chain per CTA, smem ring  (lz4b200_solo_kernel.cuh)      LZ4B200_ENC_SOLO=1|2, _SOLO_SMALL_MAX=1000000
   warp kernels matcher/emitter warps, lane groups (default)                 LZ4B200_THREAD_MIN=4e9, LZ4B200_ENC_SOLO=0
-               (global tables tagged by default; LZ4B200_ENC_GTAG=0: untagged)
+               (LZ4B200_ENC_GTAG=71: tagged table entries; LZ4B200_ENC_G16=62: two chains per matcher warp)
 Bit-exact compressed bytes in all three parse modes, exact round trips, identical error codes / expected fields."""
 import os
 
@@ -21,8 +21,10 @@ VARIANTS = {
     "thread8": {"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_SOLO": "0", "LZ4B200_ENC_THREAD_LANES": "8", "LZ4B200_DEC_THREAD_LANES": "8"},
     "thread_few": {"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_SOLO": "0", "LZ4B200_ENC_THREADS": "64", "LZ4B200_DEC_THREADS": "64"},
     "solo": {"LZ4B200_ENC_SOLO": "1", "LZ4B200_ENC_SOLO_SMALL_MAX": "1000000", "LZ4B200_THREAD_MIN": "4000000000"},
+    "solo2": {"LZ4B200_ENC_SOLO": "2", "LZ4B200_ENC_SOLO_SMALL_MAX": "1000000", "LZ4B200_THREAD_MIN": "4000000000"},
     "warp": {"LZ4B200_THREAD_MIN": "4000000000", "LZ4B200_ENC_SOLO": "0"},
-    "warp_untagged": {"LZ4B200_ENC_GTAG": "0"},
+    "warp_tagged": {"LZ4B200_ENC_GTAG": "71"},
+    "warp_half": {"LZ4B200_ENC_G16": "62"},
 }
 
 
@@ -156,7 +158,7 @@ def test_many_blocks_global_table_kernels(vctx):
     (tagged entries by default) — ragged block lengths, all three parse modes, every block compared with the oracle."""
     src = corpus.tiled("compression_66k_JSON.txt", 40 << 20)
     d = np.frombuffer(corpus.load("dickens.txt"), dtype=np.uint8)
-    src[20 << 20: 30 << 20] = d[: 10 << 20]
+    src[20 << 20: (20 << 20) + d.size] = d
     rng = np.random.default_rng(77)
     lens = rng.integers(1500, 12000, 6000).astype(np.uint32)
     lens[:64] = np.arange(64, dtype=np.uint32)

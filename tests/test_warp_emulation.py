@@ -36,7 +36,13 @@ def _last_literals(b, start):
     return bytes([min(n, 15) << 4]) + (_ext(n - 15) if n >= 15 else b"") + b[start:]
 
 
-def warp_encode(b: bytes, cont: bool = False, h5=None, stats=None) -> bytes:
+def _tag16(b, p):
+    return ((int.from_bytes(b[p:p + 4], "little") * 2246822519) & 0xFFFFFFFF) >> 16
+
+
+def warp_encode(b: bytes, cont: bool = False, h5=None, stats=None, tagged: bool = False, G: int = 32) -> bytes:
+    """tagged=True models lz4_compress_blocks_gtag: table entries are (tag << 16) | position, a probe only looks at its
+    candidate's bytes when the tags agree, and a candidate forwarded inside the batch is compared register to register."""
     n = len(b)
     if n < 13:
         return _last_literals(b, 0)
@@ -44,57 +50,72 @@ def warp_encode(b: bytes, cont: bool = False, h5=None, stats=None) -> bytes:
         h5 = n >= 65535
     H = _h5 if h5 else _h4
     tab = [INVALID if cont else 0] * 4096
+    fetched = [0]                                                # candidate fetches from memory (the traffic tags remove)
+    if tagged:
+        assert n <= 65536
+        tab = [INVALID if cont else (_tag16(b, 0) << 16)] * 4096
     last_probe, lim = n - 12, n - 6
     out = bytearray()
     anchor = cur = 0
     ri = False
     if not cont:
-        tab[H(b, 0)] = 0
+        tab[H(b, 0)] = (_tag16(b, 0) << 16) if tagged else 0
         cur = 1
+    R = range(G)
     while True:
-        base, stride = cur, 1
-        while True:                                              # one probe batch = 32 lanes
-            p = [base + i * stride for i in range(32)]
+        base, nbatch = cur, 0
+        while True:                                              # one probe batch = G lanes (32, or 16 for the half-warp kernel)
+            stride = nbatch // (32 // G) + 1                     # compress.rs:374-378: 32 probes per step value
+            p = [base + i * stride for i in R]
             term = [x > last_probe for x in p]
             if ri:                                               # re-insert of the previous sequence, before the table reads
-                tab[H(b, cur - 2)] = cur - 2
+                tab[H(b, cur - 2)] = ((cur - 2) | (_tag16(b, cur - 2) << 16)) if tagged else cur - 2
                 ri = False
-            key = [H(b, p[i]) if not term[i] else (0x10000 | i) for i in range(32)]
-            cnd = [tab[key[i]] if not term[i] else INVALID for i in range(32)]
+            key = [H(b, p[i]) if not term[i] else (0x10000 | i) for i in R]
+            cnd = [tab[key[i]] if not term[i] else INVALID for i in R]
+            tag_ok = [True] * G
+            if tagged:
+                for i in R:
+                    if cnd[i] != INVALID:
+                        tag_ok[i] = (cnd[i] >> 16) == _tag16(b, p[i])
+                        cnd[i] &= 0xFFFF
 
-            def check(i, c):
-                return (not term[i]) and c != INVALID and p[i] - c <= 65535 and b[c:c + 4] == b[p[i]:p[i] + 4]
+            def check(i, c, use_tag=True):
+                if term[i] or c == INVALID or p[i] - c > 65535 or (use_tag and not tag_ok[i]):
+                    return False
+                fetched[0] += 1
+                return b[c:c + 4] == b[p[i]:p[i] + 4]
 
-            hit = [check(i, cnd[i]) for i in range(32)]
-            w0 = hit.index(True) if True in hit else 32
+            hit = [check(i, cnd[i]) for i in R]
+            w0 = hit.index(True) if True in hit else G
             exact = w0 == 0
             if 1 <= w0 <= 3:                                     # three shuffles: keys of lanes 0..2 against lanes <= w0
                 exact = not any(key[j] == key[i] for j in range(1, w0 + 1) for i in range(j))
-            same = [[i] for i in range(32)]
+            same = [[i] for i in R]
             if not exact:                                        # match.any + forwarding of in-batch writes
-                same = [[j for j in range(32) if key[j] == key[i]] for i in range(32)]
-                prior = [[j for j in same[i] if j < i] for i in range(32)]
-                upto0 = 31 if w0 >= 31 else w0
+                same = [[j for j in R if key[j] == key[i]] for i in R]
+                prior = [[j for j in same[i] if j < i] for i in R]
+                upto0 = G - 1 if w0 >= G - 1 else w0
                 if any(prior[i] for i in range(upto0 + 1)):
-                    for i in range(32):
+                    for i in R:
                         if prior[i]:
                             cnd[i] = p[prior[i][-1]]
-                            hit[i] = check(i, cnd[i])
+                            hit[i] = check(i, cnd[i], use_tag=False)      # forwarded: compared lane to lane, no tag
                 if stats is not None:
                     stats["slow"] = stats.get("slow", 0) + 1
-            win = hit.index(True) if True in hit else 32
-            tfirst = term.index(True) if True in term else 32
+            win = hit.index(True) if True in hit else G
+            tfirst = term.index(True) if True in term else G
             if tfirst < win:                                     # compress.rs:381-384
                 return bytes(out) + _last_literals(b, anchor)
-            upto = win if win < 32 else 31
+            upto = win if win < G else G - 1
             for i in range(upto + 1):                            # commit: last writer per slot among the executed probes
                 if max(j for j in same[i] if j <= upto) == i:
-                    tab[key[i]] = p[i]
-            if win < 32:
+                    tab[key[i]] = (p[i] | (_tag16(b, p[i]) << 16)) if tagged else p[i]
+            if win < G:
                 mpos, cand = p[win], cnd[win]
                 break
-            base += 32 * stride
-            stride += 1
+            base += G * stride
+            nbatch += 1
         dist = mpos - cand
         while cand > 0 and mpos > anchor and b[mpos - 1] == b[cand - 1]:
             mpos -= 1; cand -= 1
@@ -113,6 +134,7 @@ def warp_encode(b: bytes, cont: bool = False, h5=None, stats=None) -> bytes:
         ri = True
         if stats is not None:
             stats["seqs"] = stats.get("seqs", 0) + 1
+            stats["fetched"] = fetched[0]
 
 
 def _cases():
@@ -148,3 +170,31 @@ def test_collision_path_is_exercised():
     low = np.random.default_rng(1).integers(0, 2, 30000, dtype=np.uint8).tobytes()
     assert warp_encode(low, stats=s2) == oracle.compress_block(low)
     assert s2.get("slow", 0) > 0 and s2["seqs"] > 100
+
+
+@pytest.mark.parametrize("name,data", [c for c in CASES if len(c[1]) <= 65536], ids=[c[0] for c in CASES if len(c[1]) <= 65536])
+def test_tagged_entries_keep_the_parse(name, data):
+    """lz4_compress_blocks_gtag: (tag, position) entries.  A tag mismatch proves the 4-byte comparison fails, so skipping
+    the candidate fetch cannot change the parse — in any mode, including the FRESH table whose empty slots stand for
+    position 0 and must carry position 0's tag."""
+    assert warp_encode(data, tagged=True) == oracle.compress_block(data)
+    assert warp_encode(data, cont=True, h5=True, tagged=True) == oracle.compress_block_cont(data)
+    assert warp_encode(data, cont=False, h5=True, tagged=True) == oracle.compress_block_fresh_h5(data)
+
+
+def test_tags_remove_the_false_candidate_fetches():
+    """What is left after the tag filter are (almost only) true 4-byte matches: on JSON ~18 of a batch's 32 probes really
+    match their candidate, and those candidates are consecutive addresses (one or two sectors).  The ~45 % that the tags
+    remove are the scattered ones — stale or colliding slots — each of which cost a sector of its own."""
+    data = corpus.tiled("compression_66k_JSON.txt", 65536).tobytes()
+    a, t = {}, {}
+    assert warp_encode(data, h5=True, stats=a) == warp_encode(data, h5=True, stats=t, tagged=True)
+    assert t["fetched"] < 0.65 * a["fetched"], (a["fetched"], t["fetched"])
+
+
+@pytest.mark.parametrize("name,data", [c for c in CASES if len(c[1]) <= 65536], ids=[c[0] for c in CASES if len(c[1]) <= 65536])
+def test_half_warp_batches_keep_the_parse(name, data):
+    """lz4_compress_blocks_gtab16: 16 probes per batch, two batches per step value of compress.rs:374-378."""
+    assert warp_encode(data, G=16) == oracle.compress_block(data)
+    assert warp_encode(data, cont=True, h5=True, G=16) == oracle.compress_block_cont(data)
+    assert warp_encode(data, cont=False, h5=True, G=16) == oracle.compress_block_fresh_h5(data)
