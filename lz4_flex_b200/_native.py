@@ -34,12 +34,33 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+AB_SO_PATH = os.path.join(_PKG, "liblz4b200_ab.so")
+
+
+def build_ab(force: bool = False) -> str:
+    """The A/B library: the same sources with -DLZ4B200_AB_VARIANTS, i.e. the product kernels PLUS every variant that
+    lost its measurement (thread-per-block, single-thread solo, tagged tables, v1 encoder, converged / batched decoders)
+    and the environment switches that select them.  Only tests/test_gpu_kernel_variants.py and tests/dev/* load it (through
+    LZ4B200_SO_OVERRIDE in a child process); the product library carries none of it."""
+    if not force and os.path.exists(AB_SO_PATH):
+        t = os.path.getmtime(AB_SO_PATH)
+        deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [HEADER]
+        if all(os.path.getmtime(d) <= t for d in deps):
+            return AB_SO_PATH
+    return _compile(AB_SO_PATH, ["-DLZ4B200_AB_VARIANTS"], force=True)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> lz4_flex_b200/liblz4b200.so"""
     if os.environ.get("LZ4B200_SO_OVERRIDE"):
         return SO_PATH
     if not force and not _stale():
         return SO_PATH
+    return _compile(SO_PATH, [], force, verbose)
+
+
+def _compile(out_path: str, extra: list, force: bool = False, verbose: bool = False) -> str:
+    SO_PATH = out_path
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found and liblz4b200.so is missing or stale")
@@ -49,10 +70,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with open(SO_PATH + ".lock", "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
         try:
-            if not force and not _stale():
+            if not force and out_path == globals()["SO_PATH"] and not _stale():
                 return SO_PATH
             tmp = f"{SO_PATH}.tmp{os.getpid()}"
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 if os.path.exists(tmp):

@@ -14,8 +14,12 @@
 #include <vector>
 
 #include "lz4b200_kernels.cuh"
-#include "lz4b200_thread_kernels.cuh"
 #include "lz4b200_solo_kernel.cuh"
+#ifdef LZ4B200_AB_VARIANTS
+// A/B build (lz4_flex_b200/liblz4b200_ab.so, -DLZ4B200_AB_VARIANTS): the kernels that lost their measurements stay
+// compilable and testable there (tests/test_gpu_kernel_variants.py) but are not part of the product library.
+#include "lz4b200_thread_kernels.cuh"
+#endif
 
 using namespace lz4b200;
 
@@ -253,39 +257,35 @@ struct lz4b200_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint32_t *d_tickets = nullptr;            // 3 x {next, retired}
-    int dec_ctas_per_sm = 0, enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
-    int enc_smem_kb = 0;                      // LZ4B200_ENC_SMEM_KB: shared-memory carve-out used by the encoder
+    int dec_ctas_per_sm = 0;
     int enc16s_ctas_per_sm = 0, enc32s_ctas_per_sm = 0;   // split (matcher+emitter) encoder
     int high_priority = 0;                    // lz4b200_ctx_set_priority(ctx, 1): pipeline streams get the highest priority
-    int enc_gtab = 71;                        // global-table encoder: 10*matchers + emitters per CTA (62|71); LZ4B200_ENC_GTAB=0: off
-    int enc_gtab_smem = 0;
-    int enc_gtab_carveout = -1;               // LZ4B200_ENC_GTAB_CARVEOUT=<percent of shared memory>
-    bool enc_gtab_carveout_set = false;
-    DevBuf<uint16_t> d_gtab16;
-    DevBuf<uint32_t> d_gtag32;                // tagged global tables (lz4_compress_blocks_gtag)
+    DevBuf<uint16_t> d_gtab16;                // global u16 tables (lz4_compress_blocks_gtab / _gtab16)
+    const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_g16 = 0;                          // LZ4B200_ENC_G16=10*matcher warps+emitters (62|71): half-warp matchers, 0: off
     int enc_g16_ctas = 8;                     // LZ4B200_ENC_G16_CTAS
-    int enc_gtag = 0;                         // LZ4B200_ENC_GTAG=10*matchers+emitters (71|62): tagged entries (measured slower: 19.4 vs 17.8 ms), 0: off
-    int enc_gtag_ctas = 8;                    // LZ4B200_ENC_GTAG_CTAS: CTAs per SM (tables must stay L2-resident: 16 KiB each)
+    // K1-S2 (one chain per CTA over the TMA-fed ring, lz4b200_solo_kernel.cuh): LZ4B200_ENC_SOLO=2 routes batches of
+    // blocks > 64 KiB (and batches of at most enc_solo_small_max small blocks) to it
+    int enc_solo = 0, enc_solo_ctas_per_sm = 0, enc_solo2_ctas_per_sm = 0;
+    uint32_t enc_solo_small_max = 0;
+#ifdef LZ4B200_AB_VARIANTS
+    int enc16_ctas_per_sm = 0, enc32_ctas_per_sm = 0;
+    int enc_gtab = 71;                        // LZ4B200_ENC_GTAB=10*matchers+emitters per CTA (62|71|44|151)
+    int enc_gtab_smem = 0;
     DevBuf<uint16_t> d_ttab16;                // K1-T tables
-    const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
-    int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits (A/B aid)
-    int enc_group_override = 0;               // LZ4B200_ENC_GROUP=8|16|32 (tuning aid)
-    int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM (tuning aid)
-    int dec_conv = 0;                         // LZ4B200_DEC_CONV=1: warp-converged decoder loop (A/B aid)
-    int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1 (tuning aid)
-    int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32 (tuning aid)
-    // K1-T / K2-T (one block per thread, lz4b200_thread_kernels.cuh): used for batches of at least thread_min_blocks
-    // blocks of <= 64 KiB without a dictionary.  LZ4B200_THREAD_MIN / _ENC_THREAD_LANES / _DEC_THREAD_LANES /
-    // _ENC_THREADS / _DEC_THREADS override the launch shape (tuning aids).
-    uint32_t enc_thread_min = 0xffffffffu, dec_thread_min = 0xffffffffu;   // off by default: measured slower
-    int enc_thread_lanes = 0, dec_thread_lanes = 0;   // 0: chosen from the batch size
+    DevBuf<uint32_t> d_gtag32;                // tagged global tables (lz4_compress_blocks_gtag)
+    int enc_gtag = 0;                         // LZ4B200_ENC_GTAG=71|62: tagged entries (measured slower: 19.4 vs 17.8 ms)
+    int enc_gtag_ctas = 8;
+    int enc_single_warp = 0;                  // LZ4B200_ENC_SINGLE_WARP=1: one warp searches and emits
+    int dec_ctas_override = 0;                // LZ4B200_DEC_CTAS=n CTAs per SM
+    int dec_conv = 0;                         // LZ4B200_DEC_CONV=1: warp-converged decoder loop
+    int dec_batched = 0;                      // LZ4B200_DEC_BATCHED=1
+    int dec_group_override = 0;               // LZ4B200_DEC_GROUP=4|8|16|32
+    // K1-T / K2-T (one block per thread, lz4b200_thread_kernels.cuh)
+    uint32_t enc_thread_min = 0xffffffffu, dec_thread_min = 0xffffffffu;
+    int enc_thread_lanes = 0, dec_thread_lanes = 0;
     uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
-    // K1-S (one chain per CTA in shared memory, lz4b200_solo_kernel.cuh): every batch of blocks > 64 KiB, and small
-    // batches of small blocks (fewer chains than the GPU has half-SMs).  LZ4B200_ENC_SOLO=0 disables it (A/B aid).
-    int enc_solo2_ctas_per_sm = 0;
-    int enc_solo = 0, enc_solo_ctas_per_sm = 0;                                // off by default: measured slower
-    uint32_t enc_solo_small_max = 0;          // set from the SM count at context creation
+#endif
     std::string last_error;
     uint32_t range_nb = 0;                    // lz4b200_frame_range_compress -> _pack hand-over
     const uint8_t *range_in = nullptr;
@@ -308,11 +308,10 @@ struct lz4b200_ctx {
 
 namespace {
 
-#ifndef ENC16_WARPS
-#define ENC16_WARPS 4
-#endif
-constexpr int kEnc16Warps = ENC16_WARPS;   // 8 KiB table per warp; 1-warp CTAs give the finest smem granularity
+#ifdef LZ4B200_AB_VARIANTS
+constexpr int kEnc16Warps = 4;     // v1 encoder: 8 KiB table per warp
 constexpr int kEnc32Warps = 2;     // 2 x 16 KiB tables per CTA
+#endif
 #ifndef ENC16_PAIRS
 #define ENC16_PAIRS 3
 #endif
@@ -335,10 +334,13 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
 {
     const uint32_t per_cta = kDecWarpsPerCta * (32 / G);
     uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
-    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * (ctx->dec_ctas_override ? ctx->dec_ctas_override : 16)));
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * 16));
+#ifdef LZ4B200_AB_VARIANTS
+    if (ctx->dec_ctas_override) grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->dec_ctas_override));
+    if (!a.dict_len && ctx->dec_conv) { lz4_decompress_blocks_conv<G><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a); CTX_CUDA(ctx, cudaGetLastError()); return LZ4B200_OK; }
+    if (!a.dict_len && ctx->dec_batched) { lz4_decompress_blocks<G, 1, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a); CTX_CUDA(ctx, cudaGetLastError()); return LZ4B200_OK; }
+#endif
     if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
-    else if (ctx->dec_conv) lz4_decompress_blocks_conv<G><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
-    else if (ctx->dec_batched) lz4_decompress_blocks<G, 1, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     else lz4_decompress_blocks<G, 0, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     CTX_CUDA(ctx, cudaGetLastError());
     return LZ4B200_OK;
@@ -348,14 +350,16 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
 // chains); with many blocks narrower groups cut the warp-instructions per sequence.
 int pick_dec_group(const lz4b200_ctx *ctx, uint32_t nblocks)
 {
+#ifdef LZ4B200_AB_VARIANTS
     if (ctx->dec_group_override) return ctx->dec_group_override;
-    const uint32_t warps = (uint32_t)(ctx->sm_count * ctx->dec_ctas_per_sm * kDecWarpsPerCta);
-    (void)warps;
+#endif
+    (void)ctx;
     // measured on B200, 64 KiB JSON blocks: 16 384 blocks -> G=8 4.2 ms, G=16 4.5 ms, G=32 5.8 ms
     if (nblocks >= 12288) return 8;
     return nblocks >= 4096 ? 16 : 32;
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Active lanes per warp for the thread-per-block kernels: a batch with fewer blocks than the GPU has lanes is
 // spread over more warps.
 int pick_thread_lanes(const lz4b200_ctx *ctx, uint32_t threads, int override_lanes)
@@ -374,12 +378,14 @@ lz4b200_status launch_decompress_thread(lz4b200_ctx *ctx, const BatchArgs &a, ui
     CTX_CUDA(ctx, cudaGetLastError());
     return LZ4B200_OK;
 }
+#endif
 
 lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaStream_t s, uint32_t *tickets = nullptr)
 {
     if (args.nblocks == 0) return LZ4B200_OK;
     BatchArgs a = args;
     a.tickets = tickets ? tickets : ctx->d_tickets;
+#ifdef LZ4B200_AB_VARIANTS
     if (!a.dict_len && a.nblocks >= ctx->dec_thread_min) {
         const uint32_t threads = std::min(a.nblocks, ctx->dec_thread_max);
         switch (pick_thread_lanes(ctx, threads, ctx->dec_thread_lanes)) {
@@ -388,101 +394,70 @@ lz4b200_status launch_decompress(lz4b200_ctx *ctx, const BatchArgs &args, cudaSt
         default: return launch_decompress_thread<32>(ctx, a, threads, s);
         }
     }
+    if (pick_dec_group(ctx, a.nblocks) == 4) return launch_decompress_g<4>(ctx, a, s);
+#endif
     switch (pick_dec_group(ctx, a.nblocks)) {
-    case 4: return launch_decompress_g<4>(ctx, a, s);
     case 8: return launch_decompress_g<8>(ctx, a, s);
     case 16: return launch_decompress_g<16>(ctx, a, s);
     default: return launch_decompress_g<32>(ctx, a, s);
     }
 }
 
-lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s,
-                               uint32_t *tickets = nullptr)
+// One table region per concurrently running launch (the host pipeline launches from up to 8 lanes): the ticket block
+// doubles as the region selector.
+static size_t table_slot(const lz4b200_ctx *ctx, const uint32_t *tickets)
 {
-    if (!tickets) tickets = ctx->d_tickets;
-    if (args.nblocks == 0) return LZ4B200_OK;
-    BatchArgs a = args;
-    if (!a.dict_len && ctx->enc_solo && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
-        if (ctx->enc_solo == 2) {                         // warp matcher over the ring (K1-S2)
-            const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo2_ctas_per_sm));
-            lz4_compress_blocks_solo2<<<grid, 64, kSolo2SmemBytes, s>>>(a, tickets + 4);
-            CTX_CUDA(ctx, cudaGetLastError());
-            return LZ4B200_OK;
-        }
+    return tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
+}
+
+#ifdef LZ4B200_AB_VARIANTS
+// The measured-and-rejected K1 variants.  Returns true when one of them took the batch.
+static bool launch_compress_variant(lz4b200_ctx *ctx, const BatchArgs &a, uint32_t max_in_len, cudaStream_t s, uint32_t *tickets,
+                                    lz4b200_status *st)
+{
+    *st = LZ4B200_OK;
+    if (a.dict_len) return false;
+    if (ctx->enc_solo == 1 && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
         const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm));
         lz4_compress_blocks_solo<<<grid, 64, kSoloSmemBytes, s>>>(a, tickets + 4);
-        CTX_CUDA(ctx, cudaGetLastError());
-        return LZ4B200_OK;
+        if (!ctx->check(cudaGetLastError(), "solo launch")) *st = LZ4B200_CUDA_ERROR;
+        return true;
     }
-    if (!a.dict_len && max_in_len != 0 && max_in_len <= 65536u && a.nblocks >= ctx->enc_thread_min) {
-        // K1-T: one block per thread, 8 KiB table per thread in global memory (one region per concurrent launch)
+    if (max_in_len != 0 && max_in_len <= 65536u && a.nblocks >= ctx->enc_thread_min) {
+        // K1-T: one block per thread, 8 KiB table per thread in global memory
         const uint32_t threads = std::min(a.nblocks, ctx->enc_thread_max);
         const size_t region = (size_t)ctx->enc_thread_max * 4096u;                  // u16 entries
-        const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
-        if (!ctx->check(ctx->d_ttab16.reserve(region * (slot ? 9u : 1u)), "thread tables")) return LZ4B200_CUDA_ERROR;
+        const size_t slot = table_slot(ctx, tickets);
+        if (!ctx->check(ctx->d_ttab16.reserve(region * (slot ? 9u : 1u)), "thread tables")) { *st = LZ4B200_CUDA_ERROR; return true; }
         uint16_t *gt = ctx->d_ttab16.p + slot * region;
         const int lanes = pick_thread_lanes(ctx, threads, ctx->enc_thread_lanes);
         const uint32_t per_cta = kThreadCtaWarps * lanes, grid = (threads + per_cta - 1) / per_cta;
         if (lanes == 8) lz4_compress_blocks_thread<8><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
         else if (lanes == 16) lz4_compress_blocks_thread<16><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
         else lz4_compress_blocks_thread<32><<<grid, kThreadCtaWarps * 32, 0, s>>>(a, tickets + 2, gt);
-        CTX_CUDA(ctx, cudaGetLastError());
-        return LZ4B200_OK;
+        if (!ctx->check(cudaGetLastError(), "thread launch")) *st = LZ4B200_CUDA_ERROR;
+        return true;
     }
-    // blocks <= 64 KiB: u16 tables; larger: u32 tables.  Unknown mix (max_in_len == 0): both.
-    {
-        uint32_t want = (a.nblocks + kEnc16Warps - 1) / kEnc16Warps;
-        uint32_t per_sm = (uint32_t)ctx->enc16_ctas_per_sm;
-        if (ctx->enc_smem_kb) {                                 // tuning aid: trade resident tables for L1 capacity
-            const uint32_t cta_kb = kEnc16Warps * 8 + 1;
-            per_sm = std::max<uint32_t>(1, std::min<uint32_t>(per_sm, (uint32_t)ctx->enc_smem_kb / cta_kb));
-        }
-        uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * per_sm);
-#if ENC_SPLIT
-        // Global-table encoder when the batch has more blocks than the shared-memory-table kernel keeps in flight
-        // (24 per SM): 56 slower chains per SM then beat 24 faster ones (17.3 vs 20.1 ms per GiB of 64 KiB blocks);
-        // with fewer blocks the shorter chain of the shared-memory tables wins.
-        if (ctx->enc_g16 && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
-            const int m = ctx->enc_g16 / 10;                                          // matcher warps per CTA, 2 chains each
-            want = (a.nblocks + 2 * m - 1) / (2 * m);
-            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
-            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries, 8 CTAs x 16 chains max
-            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
-            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab16")) return LZ4B200_CUDA_ERROR;
-            uint16_t *gt = ctx->d_gtab16.p + slot * region;
-            if (m == 7) lz4_compress_blocks_gtab16<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-            else lz4_compress_blocks_gtab16<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-        } else
-        if (ctx->enc_gtag && ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+    if (max_in_len != 0 && max_in_len <= 65536u && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+        const size_t slot = table_slot(ctx, tickets);
+        if (ctx->enc_gtag) {                                                         // tagged (tag, position) entries
             const int m = ctx->enc_gtag / 10;
-            want = (a.nblocks + m - 1) / m;
-            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc_gtag_ctas));
-            const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;             // u32 entries, 8 CTAs x 8 warps max
-            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
-            if (!ctx->check(ctx->d_gtag32.reserve(region * 9u), "gtag")) return LZ4B200_CUDA_ERROR;
+            const uint32_t grid = std::min<uint32_t>((a.nblocks + m - 1) / m, (uint32_t)(ctx->sm_count * ctx->enc_gtag_ctas));
+            const size_t region = (size_t)ctx->sm_count * 8u * 8u * 4096u;
+            if (!ctx->check(ctx->d_gtag32.reserve(region * 9u), "gtag")) { *st = LZ4B200_CUDA_ERROR; return true; }
             uint32_t *gt = ctx->d_gtag32.p + slot * region;
             if (m == 6) lz4_compress_blocks_gtag<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else lz4_compress_blocks_gtag<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-        } else
-        if (ctx->enc_gtab && !a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
-            // global-table encoder: 8 warps per CTA, 8 CTAs per SM
-            const int m = ctx->enc_gtab / 10, e = ctx->enc_gtab % 10;
-            want = (a.nblocks + m - 1) / m;
-            grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * (m == 15 ? 4u : 8u));
-            // one table region per concurrently running launch (the host pipeline launches from up to 8 lanes):
-            // the ticket block doubles as the region selector
-            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries (sized for the half-warp kernel too)
-            const size_t slot = tickets == ctx->d_tickets ? 0 : 1 + ((size_t)(tickets - ctx->pipe_tickets) / 8u) % 8u;
-            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
+            if (!ctx->check(cudaGetLastError(), "gtag launch")) *st = LZ4B200_CUDA_ERROR;
+            return true;
+        }
+        const int m = ctx->enc_gtab / 10, e = ctx->enc_gtab % 10, ks = ctx->enc_gtab_smem;
+        if (ctx->enc_gtab && (m != 7 || e != 1 || ks)) {                              // other global-table CTA shapes
+            const uint32_t want = (a.nblocks + m - 1) / m;
+            uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * (m == 15 ? 4u : 8u));
+            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;
+            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) { *st = LZ4B200_CUDA_ERROR; return true; }
             uint16_t *gt = ctx->d_gtab16.p + slot * region;
-            // LZ4B200_ENC_GTAB = 10*matchers + emitters per CTA; LZ4B200_ENC_GTAB_SMEM = how many of the matchers keep
-            // their table in shared memory (0, 2 or 3)
-            const int ks = ctx->enc_gtab_smem;
-            if (ctx->enc_gtab_carveout >= 0 && !ctx->enc_gtab_carveout_set) {      // tuning aid: L1 vs shared memory split
-                cudaFuncSetAttribute(lz4_compress_blocks_gtab<uint16_t, 7, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     ctx->enc_gtab_carveout);
-                ctx->enc_gtab_carveout_set = true;
-            }
             if (m == 15) lz4_compress_blocks_gtab<uint16_t, 15, 1, 0><<<grid, 512, 0, s>>>(a, tickets + 2, gt);
             else if (m == 6 && e == 2) lz4_compress_blocks_gtab<uint16_t, 6, 2, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             else if (m == 4 && e == 4) lz4_compress_blocks_gtab<uint16_t, 4, 4, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
@@ -490,40 +465,83 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             else if (ks == 3) {
                 grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * 7u);
                 lz4_compress_blocks_gtab<uint16_t, 7, 1, 3><<<grid, 256, 3 * 8192, s>>>(a, tickets + 2, gt);
-            } else lz4_compress_blocks_gtab<uint16_t, 7, 1, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-        } else
-        if (!ctx->enc_single_warp || a.dict_len) {
-            want = (a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs;
-            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
+            } else return false;
+            if (!ctx->check(cudaGetLastError(), "gtab launch")) *st = LZ4B200_CUDA_ERROR;
+            return true;
+        }
+    }
+    if (ctx->enc_single_warp) {                                                      // v1: one warp searches and emits
+        if (max_in_len == 0 || max_in_len <= 65536u) {
+            const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc16Warps - 1) / kEnc16Warps, (uint32_t)ctx->sm_count * (uint32_t)ctx->enc16_ctas_per_sm);
+            lz4_compress_blocks<uint16_t, kEnc16Warps><<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, tickets + 2);
+        }
+        if (max_in_len == 0 || max_in_len > 65536u) {
+            const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc32Warps - 1) / kEnc32Warps, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
+            lz4_compress_blocks<uint32_t, kEnc32Warps><<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, tickets + 4);
+        }
+        if (!ctx->check(cudaGetLastError(), "v1 launch")) *st = LZ4B200_CUDA_ERROR;
+        return true;
+    }
+    return false;
+}
+#endif
+
+// K1 launcher.  Blocks <= 64 KiB: u16 tables; larger: u32 tables; unknown mix (max_in_len == 0): both kernels run over
+// the same ticket space and each skips the other's blocks.
+//   many small blocks (> 24 per SM, no dictionary)  -> global tables (56 chains per SM; half-warp matchers: 96+)
+//   fewer / dictionary                              -> shared-memory tables, matcher + emitter pairs
+//   blocks > 64 KiB without dictionary              -> one chain per CTA over the TMA-fed ring when enabled
+lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t max_in_len, cudaStream_t s,
+                               uint32_t *tickets = nullptr)
+{
+    if (!tickets) tickets = ctx->d_tickets;
+    if (args.nblocks == 0) return LZ4B200_OK;
+    const BatchArgs &a = args;
+#ifdef LZ4B200_AB_VARIANTS
+    {
+        lz4b200_status vst;
+        if (launch_compress_variant(ctx, a, max_in_len, s, tickets, &vst)) return vst;
+    }
+#endif
+    if (!a.dict_len && ctx->enc_solo == 2 && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
+        const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo2_ctas_per_sm));
+        lz4_compress_blocks_solo2<<<grid, 64, kSolo2SmemBytes, s>>>(a, tickets + 4);
+        CTX_CUDA(ctx, cudaGetLastError());
+        return LZ4B200_OK;
+    }
+    {                                                       // u16 tables: every block with input (+ dictionary) <= 64 KiB
+        if (!a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
+            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries: 8 CTAs x 16 chains
+            if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
+            uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
+            if (ctx->enc_g16) {                                                      // two chains per matcher warp
+                const int m = ctx->enc_g16 / 10;
+                const uint32_t grid = std::min<uint32_t>((a.nblocks + 2 * m - 1) / (2 * m), (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
+                if (m == 7) lz4_compress_blocks_gtab16<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                else lz4_compress_blocks_gtab16<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            } else {
+                const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * 8u);
+                lz4_compress_blocks_gtab<uint16_t, 7, 1, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            }
+        } else {
+            const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
             if (a.dict_len)
                 lz4_compress_blocks_split<uint16_t, kEnc16Pairs, true>
                     <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
             else
                 lz4_compress_blocks_split<uint16_t, kEnc16Pairs, false>
                     <<<grid, kEnc16Pairs * 64, split_smem_bytes<uint16_t, kEnc16Pairs>(), s>>>(a, tickets + 2);
-        } else
-#endif
-        lz4_compress_blocks<uint16_t, kEnc16Warps>
-            <<<grid, kEnc16Warps * 32, kEnc16Warps * 4096 * sizeof(uint16_t), s>>>(a, tickets + 2);
+        }
         CTX_CUDA(ctx, cudaGetLastError());
     }
     if (max_in_len == 0 || (uint64_t)max_in_len + a.dict_len > 65536u) {
-        uint32_t want = (a.nblocks + kEnc32Warps - 1) / kEnc32Warps;
-        uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32_ctas_per_sm));
-#if ENC_SPLIT
-        if (!ctx->enc_single_warp || a.dict_len) {
-            want = (a.nblocks + kEnc32Pairs - 1) / kEnc32Pairs;
-            grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->enc32s_ctas_per_sm));
-            if (a.dict_len)
-                lz4_compress_blocks_split<uint32_t, kEnc32Pairs, true>
-                    <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
-            else
-                lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>
-                    <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
-        } else
-#endif
-        lz4_compress_blocks<uint32_t, kEnc32Warps>
-            <<<grid, kEnc32Warps * 32, kEnc32Warps * 4096 * sizeof(uint32_t), s>>>(a, tickets + 4);
+        const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc32Pairs - 1) / kEnc32Pairs, (uint32_t)(ctx->sm_count * ctx->enc32s_ctas_per_sm));
+        if (a.dict_len)
+            lz4_compress_blocks_split<uint32_t, kEnc32Pairs, true>
+                <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
+        else
+            lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>
+                <<<grid, kEnc32Pairs * 64, split_smem_bytes<uint32_t, kEnc32Pairs>(), s>>>(a, tickets + 4);
         CTX_CUDA(ctx, cudaGetLastError());
     }
     return LZ4B200_OK;
@@ -593,76 +611,65 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dec_ctas_per_sm, lz4_decompress_blocks<8, 0, false>,
                                                                       kDecWarpsPerCta * 32, 0), "occupancy dec") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc16s_ctas_per_sm, lz4_compress_blocks_split<uint16_t, kEnc16Pairs, false>, kEnc16Pairs * 64,
+                            split_smem_bytes<uint16_t, kEnc16Pairs>()), "occupancy enc16 split") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                            &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>, kEnc32Pairs * 64,
+                            split_smem_bytes<uint32_t, kEnc32Pairs>()), "occupancy enc32 split") &&
+             ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kSolo2SmemBytes), "solo2 smem") &&
+             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo2_ctas_per_sm, lz4_compress_blocks_solo2, 64,
+                                                                      kSolo2SmemBytes), "occupancy solo2");
+        ctx->enc_solo_small_max = (uint32_t)(ctx->sm_count * std::max(1, ctx->enc_solo2_ctas_per_sm));
+    }
+#ifdef LZ4B200_AB_VARIANTS
+    if (ok) {
+        ok = ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                             &ctx->enc16_ctas_per_sm, lz4_compress_blocks<uint16_t, kEnc16Warps>, kEnc16Warps * 32,
                             kEnc16Warps * 4096 * sizeof(uint16_t)), "occupancy enc16") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                             &ctx->enc32_ctas_per_sm, lz4_compress_blocks<uint32_t, kEnc32Warps>, kEnc32Warps * 32,
                             kEnc32Warps * 4096 * sizeof(uint32_t)), "occupancy enc32") &&
-             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc16s_ctas_per_sm, lz4_compress_blocks_split<uint16_t, kEnc16Pairs, false>, kEnc16Pairs * 64,
-                            split_smem_bytes<uint16_t, kEnc16Pairs>()), "occupancy enc16 split") &&
-             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                            &ctx->enc32s_ctas_per_sm, lz4_compress_blocks_split<uint32_t, kEnc32Pairs, false>, kEnc32Pairs * 64,
-                            split_smem_bytes<uint32_t, kEnc32Pairs>()), "occupancy enc32 split");
-    }
-    if (ok) {
-        ok = ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo, cudaFuncAttributeMaxDynamicSharedMemorySize,
+             ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)kSoloSmemBytes), "solo smem") &&
              ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo_ctas_per_sm, lz4_compress_blocks_solo, 64,
                                                                       kSoloSmemBytes), "occupancy solo");
-        ok = ok && ctx->check(cudaFuncSetAttribute(lz4_compress_blocks_solo2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)kSolo2SmemBytes), "solo2 smem") &&
-             ctx->check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_solo2_ctas_per_sm, lz4_compress_blocks_solo2, 64,
-                                                                      kSolo2SmemBytes), "occupancy solo2");
-        ctx->enc_solo_small_max = (uint32_t)(ctx->sm_count * ctx->enc_solo_ctas_per_sm);
     }
-    if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16_ctas_per_sm < 1 || ctx->enc32_ctas_per_sm < 1) {
+#endif
+    if (!ok || ctx->dec_ctas_per_sm < 1 || ctx->enc16s_ctas_per_sm < 1 || ctx->enc32s_ctas_per_sm < 1) {
         fprintf(stderr, "lz4b200: context creation failed: %s\n", ctx->last_error.c_str());
         lz4b200_ctx_destroy(ctx);
         return LZ4B200_CUDA_ERROR;
     }
-    if (const char *g = getenv("LZ4B200_ENC_SMEM_KB")) {
-        ctx->enc_smem_kb = atoi(g);
-        if (ctx->enc_smem_kb > 0)
-            cudaFuncSetAttribute(lz4_compress_blocks<uint16_t, kEnc16Warps>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 std::min(100, ctx->enc_smem_kb * 100 / 228));
-    }
-    if (const char *g = getenv("LZ4B200_ENC_GROUP")) {
-        int v = atoi(g);
-        if (v == 8 || v == 16 || v == 32) ctx->enc_group_override = v;
-    }
-    if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
-    if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
     // The global-table encoders mark their table accesses L2::evict_last; how much of the L2 such lines may occupy is the
-    // device's persisting-L2 limit (0 by default: the hint is then ignored).
-    {
+    // device's persisting-L2 limit (LZ4B200_L2_PERSIST_MB sets it; unset = leave the process's setting alone).
+    if (const char *g = getenv("LZ4B200_L2_PERSIST_MB")) {
         int maxp = 0;
         cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
-        long want_mb = -1;
-        if (const char *g = getenv("LZ4B200_L2_PERSIST_MB")) want_mb = atol(g);
-        if (want_mb >= 0) {
-            size_t bytes = std::min<size_t>((size_t)want_mb << 20, (size_t)maxp);
-            cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
-            if (getenv("LZ4B200_DEBUG"))
-                fprintf(stderr, "lz4b200: persisting L2 limit %zu of max %d bytes: %s\n", bytes, maxp, cudaGetErrorString(e));
-        }
+        const size_t bytes = std::min<size_t>((size_t)std::max(0L, atol(g)) << 20, (size_t)maxp);
+        const cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+        if (getenv("LZ4B200_DEBUG"))
+            fprintf(stderr, "lz4b200: persisting L2 limit %zu of max %d bytes: %s\n", bytes, maxp, cudaGetErrorString(e));
     }
     if (const char *g = getenv("LZ4B200_ENC_G16")) ctx->enc_g16 = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_G16_CTAS")) ctx->enc_g16_ctas = std::max(1, std::min(8, atoi(g)));
+    if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
+    if (ctx->enc_solo2_ctas_per_sm < 1 && ctx->enc_solo == 2) ctx->enc_solo = 0;
+    if (getenv("LZ4B200_DEBUG"))
+        fprintf(stderr, "lz4b200: SMs %d, CTAs/SM: dec %d, enc16-split %d (x%d pairs), enc32-split %d (x%d pairs), solo2 %d\n",
+                ctx->sm_count, ctx->dec_ctas_per_sm, ctx->enc16s_ctas_per_sm, kEnc16Pairs, ctx->enc32s_ctas_per_sm, kEnc32Pairs,
+                ctx->enc_solo2_ctas_per_sm);
+#ifdef LZ4B200_AB_VARIANTS
+    if (ctx->enc_solo == 1 && ctx->enc_solo_ctas_per_sm < 1) ctx->enc_solo = 0;
+    if (const char *g = getenv("LZ4B200_ENC_SINGLE_WARP")) ctx->enc_single_warp = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_GTAB")) ctx->enc_gtab = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAG")) ctx->enc_gtag = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_GTAG_CTAS")) ctx->enc_gtag_ctas = std::max(1, std::min(8, atoi(g)));
     if (const char *g = getenv("LZ4B200_ENC_GTAB_SMEM")) ctx->enc_gtab_smem = atoi(g);
-    if (const char *g = getenv("LZ4B200_ENC_GTAB_CARVEOUT")) ctx->enc_gtab_carveout = atoi(g);
-    if (getenv("LZ4B200_DEBUG"))
-        fprintf(stderr, "lz4b200: SMs %d, CTAs/SM: dec %d, enc16 %d, enc32 %d, enc16-split %d (x%d pairs), enc32-split %d (x%d pairs)\n",
-                ctx->sm_count, ctx->dec_ctas_per_sm, ctx->enc16_ctas_per_sm, ctx->enc32_ctas_per_sm,
-                ctx->enc16s_ctas_per_sm, kEnc16Pairs, ctx->enc32s_ctas_per_sm, kEnc32Pairs);
     if (const char *g = getenv("LZ4B200_DEC_CTAS")) ctx->dec_ctas_override = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_BATCHED")) ctx->dec_batched = atoi(g);
     if (const char *g = getenv("LZ4B200_DEC_CONV")) ctx->dec_conv = atoi(g);
-    if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
-    if (ctx->enc_solo_ctas_per_sm < 1 || ctx->enc_solo2_ctas_per_sm < 1) ctx->enc_solo = 0;
-    if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_THREAD_MIN")) ctx->enc_thread_min = ctx->dec_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_ENC_THREAD_MIN")) ctx->enc_thread_min = (uint32_t)atoll(g);
     if (const char *g = getenv("LZ4B200_DEC_THREAD_MIN")) ctx->dec_thread_min = (uint32_t)atoll(g);
@@ -674,6 +681,9 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
         int v = atoi(g);
         if (v == 4 || v == 8 || v == 16 || v == 32) ctx->dec_group_override = v;
     }
+#else
+    if (ctx->enc_solo == 1) ctx->enc_solo = 0;               // the single-thread solo kernel only exists in the A/B build
+#endif
     *out = ctx;
     return LZ4B200_OK;
 }
@@ -690,7 +700,10 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx)
     ctx->d_off_b.release();
     ctx->d_in_len.release(); ctx->d_out_cap.release(); ctx->d_out_len.release(); ctx->d_info.release();
     ctx->d_seg_size.release(); ctx->d_payload_len.release(); ctx->d_status.release();
-    ctx->d_gtab16.release(); ctx->d_ttab16.release(); ctx->d_gtag32.release();
+    ctx->d_gtab16.release();
+#ifdef LZ4B200_AB_VARIANTS
+    ctx->d_ttab16.release(); ctx->d_gtag32.release();
+#endif
     delete ctx;
 }
 

@@ -847,6 +847,7 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
     retire_warp(tickets, gridDim.x * kM);
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Tagged global tables (kTag, see match_block): kM matchers + kE emitters per CTA, 16 KiB of (tag, position) entries per
 // matcher in global memory.  Blocks of at most 65 536 bytes.
 template <int kM, int kE>
@@ -872,6 +873,8 @@ lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
     matcher_loop<uint32_t, true, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
     retire_warp(tickets, gridDim.x * kM);
 }
+
+#endif  // LZ4B200_AB_VARIANTS
 
 // =============================================================================================
 // Half-warp matchers (lz4_compress_blocks_gtab16): TWO chains per matcher warp, 16 lanes each.

@@ -244,6 +244,7 @@ __device__ __forceinline__ int decode_sequence_checked(const uint8_t *__restrict
     return 0;
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Decodes one block with G lanes.  The token chain is walked kSeqBatch sequences ahead; the byte
 // copies of those sequences are then issued together: all literal runs and every match whose source
 // lies entirely before the batch (the common case: SURVEY.md §7.2, DESIGN.md "K2") are loaded
@@ -357,6 +358,8 @@ __device__ __forceinline__ DecResult decode_block(const uint8_t *__restrict__ sr
     r.written = op;
     return r;
 }
+
+#endif  // LZ4B200_AB_VARIANTS
 
 // Simple walk: one sequence at a time (fast path + checked path).
 //
@@ -627,11 +630,17 @@ lz4_decompress_blocks(BatchArgs a)
         if (sub == 0) b = atomicAdd(&a.tickets[0], 1u);
         b = __shfl_sync(gmask, b, leader);
         if (b >= a.nblocks) break;
+#ifdef LZ4B200_AB_VARIANTS
         DecResult r = kBatched
             ? decode_block<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask,
                               kDict ? a.dict : nullptr, kDict ? a.dict_len : 0u)
             : decode_block_simple<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask,
                                      kDict ? a.dict : nullptr, kDict ? a.dict_len : 0u);
+#else
+        static_assert(kBatched == 0, "the batched walk only exists in the A/B build");
+        DecResult r = decode_block_simple<G>(a.in + a.in_off[b], a.in_len[b], a.out + a.out_off[b], a.out_cap[b], sub, gmask,
+                                             kDict ? a.dict : nullptr, kDict ? a.dict_len : 0u);
+#endif
         if (sub == 0) {
             a.out_len[b] = r.status == LZ4B200_OK ? r.written : 0u;
             a.status[b] = r.status;
@@ -648,6 +657,7 @@ lz4_decompress_blocks(BatchArgs a)
     }
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Converged variant of the decoder (A/B: LZ4B200_DEC_CONV=1).  The plain kernel gives each lane group its own
 // block loop, so the 32/G groups of a warp drift apart and serialise (21.7 of 32 lanes active per instruction).
 // Here the warp runs ONE loop: every iteration each group decodes one sequence of its current block (or fetches a
@@ -767,6 +777,8 @@ lz4_decompress_blocks_conv(BatchArgs a)
     }
 }
 
+#endif  // LZ4B200_AB_VARIANTS
+
 // =============================================================================================
 // K1: encode one block with one warp — exact emulation of the reference's sequential greedy
 // parse.  The next 32 probe positions of the probe loop (compress.rs:373-439) are evaluated by
@@ -817,6 +829,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Single-warp encoder (one warp searches and emits); kept selectable (ENC_SPLIT=0) for A/B runs.
 template <typename TabT>
 __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ src, uint32_t n, uint8_t *dst,
@@ -935,11 +948,14 @@ __device__ __forceinline__ uint32_t encode_block_v1(const uint8_t *__restrict__ 
 }
 
 
+#endif  // LZ4B200_AB_VARIANTS
+
 __device__ __forceinline__ uint64_t max_output_size_dev(uint32_t n)
 {
     return 20ull + ((uint64_t)n * 110ull) / 100ull;
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // One CTA = kWarps warps, each with a private 4096-slot table in shared memory.  Blocks of up to
 // 65 536 bytes use the TabT=uint16_t instantiation (8 KiB per table), larger ones uint32_t (16 KiB);
 // the host launches both over the same ticket space and each instantiation skips the blocks that
@@ -968,6 +984,8 @@ lz4_compress_blocks(BatchArgs a, uint32_t *tickets)
     }
     retire_warp(tickets, total_warps);
 }
+
+#endif  // LZ4B200_AB_VARIANTS
 
 }  // namespace lz4b200
 

@@ -17,6 +17,7 @@
 
 namespace lz4b200 {
 
+#ifdef LZ4B200_AB_VARIANTS
 // Single-thread producer side of the tuple queue (same protocol as SeqProducer, lz4b200_enc_split.cuh).
 struct SoloSink {
     uint4 *q;
@@ -107,6 +108,8 @@ lz4_compress_blocks_solo(BatchArgs a, uint32_t *tickets)
         __threadfence();
     }
 }
+
+#endif  // LZ4B200_AB_VARIANTS
 
 // =============================================================================================
 // K1-S2: the same idea with the WARP matcher.  The single-thread matcher above pays ~5 cycles per dependent instruction

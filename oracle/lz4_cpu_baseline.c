@@ -126,41 +126,33 @@ int lz4cpu_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t ca
     for (;;) {
         const uint8_t tok = in[ip++];
         size_t lit = tok >> 4, mlen = (size_t)(tok & 15) + 4;
-        /* hot loop (decompress.rs:259-328): no length extension, room for the unconditional copies */
-        if (lit != 15 && mlen != 19 && n - ip >= 19 && cap - op >= 35) {
+        /* literals: up to 14 of them are one unconditional 16-byte copy when both buffers have the room (decompress.rs:
+         * 259-275); the room also rules out every literal-side error and the end of the block */
+        if (__builtin_expect(lit != 15 && n - ip >= 16 && cap - op >= 16, 1)) {
             cp16(out + op, in + ip);
             ip += lit; op += lit;
-            const size_t dist = (size_t)in[ip] | ((size_t)in[ip + 1] << 8);
-            ip += 2;
-            if (dist == 0) return LZ4O_ERR_OFFSET_ZERO;
-            if (dist > op) return LZ4O_ERR_OFFSET_OOB;
-            const uint8_t *from = out + op - dist;
-            if (dist >= 16) { cp16(out + op, from); memcpy(out + op + 16, from + 16, 2); }
-            else if (dist >= 8) { cp8(out + op, from); cp8(out + op + 8, from + 8); memcpy(out + op + 16, from + 16, 2); }
-            else for (size_t i = 0; i < mlen; i++) out[op + i] = from[i];
-            op += mlen;
-            continue;
-        }
-        if (lit) {
-            if (lit == 15) {
-                for (;;) {
-                    if (ip >= n) return LZ4O_ERR_EXPECTED_ANOTHER_BYTE;
-                    const uint8_t b = in[ip++];
-                    lit += b;
-                    if (b != 255) break;
+        } else {
+            if (lit) {
+                if (lit == 15) {
+                    for (;;) {
+                        if (ip >= n) return LZ4O_ERR_EXPECTED_ANOTHER_BYTE;
+                        const uint8_t b = in[ip++];
+                        lit += b;
+                        if (b != 255) break;
+                    }
                 }
+                if (lit > n - ip) return LZ4O_ERR_LITERAL_OOB;
+                if (lit > cap - op) { *err_expected = op + lit; *err_actual = cap; return LZ4O_ERR_OUTPUT_TOO_SMALL; }
+                if (n - ip >= lit + 16 && cap - op >= lit + 16) {
+                    for (size_t i = 0; i < lit; i += 16) cp16(out + op + i, in + ip + i);
+                } else {
+                    memcpy(out + op, in + ip, lit);
+                }
+                ip += lit; op += lit;
             }
-            if (lit > n - ip) return LZ4O_ERR_LITERAL_OOB;
-            if (lit > cap - op) { *err_expected = op + lit; *err_actual = cap; return LZ4O_ERR_OUTPUT_TOO_SMALL; }
-            if (n - ip >= lit + 16 && cap - op >= lit + 16) {
-                for (size_t i = 0; i < lit; i += 16) cp16(out + op + i, in + ip + i);
-            } else {
-                memcpy(out + op, in + ip, lit);
-            }
-            ip += lit; op += lit;
+            if (ip >= n) break;
+            if (n - ip < 2) return LZ4O_ERR_EXPECTED_ANOTHER_BYTE;
         }
-        if (ip >= n) break;
-        if (n - ip < 2) return LZ4O_ERR_EXPECTED_ANOTHER_BYTE;
         const size_t dist = (size_t)in[ip] | ((size_t)in[ip + 1] << 8);
         ip += 2;
         if (dist == 0) return LZ4O_ERR_OFFSET_ZERO;
@@ -177,8 +169,9 @@ int lz4cpu_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t ca
         {
             uint8_t *to = out + op;
             const uint8_t *from = to - dist;
-            if (dist >= 16 && cap - op >= mlen + 16) {
-                for (size_t i = 0; i < mlen; i += 16) cp16(to + i, from + i);
+            if (__builtin_expect(dist >= 16 && cap - op >= mlen + 16, 1)) {      /* duplicate: 16-byte chunks (decompress.rs:11-35) */
+                cp16(to, from);
+                if (mlen > 16) { cp16(to + 16, from + 16); for (size_t i = 32; i < mlen; i += 16) cp16(to + i, from + i); }
             } else if (dist >= 8 && cap - op >= mlen + 8) {
                 for (size_t i = 0; i < mlen; i += 8) cp8(to + i, from + i);
             } else if (dist == 1) {
@@ -186,7 +179,7 @@ int lz4cpu_decompress_block(const uint8_t *in, size_t n, uint8_t *out, size_t ca
             } else if (dist >= mlen) {
                 memcpy(to, from, mlen);
             } else {
-                for (size_t i = 0; i < mlen; i++) to[i] = from[i];
+                for (size_t i = 0; i < mlen; i++) to[i] = from[i];               /* duplicate_overlapping: decompress.rs:57-82 */
             }
         }
         op += mlen;

@@ -5,6 +5,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import numpy as np
 import torch
 import oracle
+from lz4_flex_b200 import _native
+if "LZ4B200_SO_OVERRIDE" not in os.environ:                  # the A/B library carries every variant and its switches
+    os.environ["LZ4B200_SO_OVERRIDE"] = _native.build_ab()
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 from lz4_flex_b200 import block, corpus
 
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
@@ -35,7 +39,7 @@ d_back = torch.zeros(NB * BS, dtype=torch.uint8, device=dev)
 
 def run(env, label, iters=5):
     for k in list(os.environ):
-        if k.startswith("LZ4B200_"):
+        if k.startswith("LZ4B200_") and k != "LZ4B200_SO_OVERRIDE":
             del os.environ[k]
     os.environ.update(env)
     ctx = block.Context(0)
