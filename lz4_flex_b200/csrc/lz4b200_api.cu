@@ -262,7 +262,7 @@ struct lz4b200_ctx {
     int high_priority = 0;                    // lz4b200_ctx_set_priority(ctx, 1): pipeline streams get the highest priority
     DevBuf<uint16_t> d_gtab16;                // global u16 tables (lz4_compress_blocks_gtab / _gtab16)
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
-    int enc_g16 = 0;                          // LZ4B200_ENC_G16=10*matcher warps+emitters (62|71): half-warp matchers, 0: off
+    int enc_g16 = 0;                          // LZ4B200_ENC_G16=62|71 (16-lane groups) or 862|871 (8-lane groups): lane-group matchers, 0: off
     int enc_g16_ctas = 8;                     // LZ4B200_ENC_G16_CTAS
     // K1-S2 (one chain per CTA over the TMA-fed ring, lz4b200_solo_kernel.cuh): LZ4B200_ENC_SOLO=2 routes batches of
     // blocks > 64 KiB (and batches of at most enc_solo_small_max small blocks) to it
@@ -455,7 +455,7 @@ static bool launch_compress_variant(lz4b200_ctx *ctx, const BatchArgs &a, uint32
         if (ctx->enc_gtab && (m != 7 || e != 1 || ks)) {                              // other global-table CTA shapes
             const uint32_t want = (a.nblocks + m - 1) / m;
             uint32_t grid = std::min<uint32_t>(want, (uint32_t)ctx->sm_count * (m == 15 ? 4u : 8u));
-            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;
+            const size_t region = (size_t)ctx->sm_count * 8u * 28u * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) { *st = LZ4B200_CUDA_ERROR; return true; }
             uint16_t *gt = ctx->d_gtab16.p + slot * region;
             if (m == 15) lz4_compress_blocks_gtab<uint16_t, 15, 1, 0><<<grid, 512, 0, s>>>(a, tickets + 2, gt);
@@ -511,14 +511,17 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     }
     {                                                       // u16 tables: every block with input (+ dictionary) <= 64 KiB
         if (!a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
-            const size_t region = (size_t)ctx->sm_count * 8u * 16u * 4096u;            // u16 entries: 8 CTAs x 16 chains
+            const size_t region = (size_t)ctx->sm_count * 8u * 28u * 4096u;            // u16 entries: 8 CTAs x up to 28 chains
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
-            if (ctx->enc_g16) {                                                      // two chains per matcher warp
-                const int m = ctx->enc_g16 / 10;
-                const uint32_t grid = std::min<uint32_t>((a.nblocks + 2 * m - 1) / (2 * m), (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
-                if (m == 7) lz4_compress_blocks_gtab16<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-                else lz4_compress_blocks_gtab16<6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+            if (ctx->enc_g16) {                                                      // 2 or 4 chains per matcher warp
+                const int m = (ctx->enc_g16 % 100) / 10, gsz = ctx->enc_g16 >= 800 ? 8 : 16;   // 62 | 71 (G = 16), 862 | 871 (G = 8)
+                const int per_cta = (32 / gsz) * m;
+                const uint32_t grid = std::min<uint32_t>((a.nblocks + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
+                if (gsz == 8 && m == 7) lz4_compress_blocks_gtabg<8, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                else if (gsz == 8) lz4_compress_blocks_gtabg<8, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                else if (m == 7) lz4_compress_blocks_gtabg<16, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                else lz4_compress_blocks_gtabg<16, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
             } else {
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * 8u);
                 lz4_compress_blocks_gtab<uint16_t, 7, 1, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);

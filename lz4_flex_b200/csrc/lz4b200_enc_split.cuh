@@ -886,21 +886,25 @@ lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
 // batch).  A batch is 16 probes (P(hit within 16) = 97 % on JSON, parse statistics in DESIGN.md), so the step rule of
 // compress.rs:374-378 (32 probes per stride value) takes two batches per stride.
 // =============================================================================================
-struct HalfWarp {
+template <int G>
+struct LaneGroup {                               // G = 16 or 8 consecutive lanes of a warp
+    static constexpr uint32_t kAll = (1u << G) - 1u;
     uint32_t sub, gshift, gmask;
-    __device__ __forceinline__ explicit HalfWarp(uint32_t lane) : sub(lane & 15u), gshift(lane & 16u), gmask(0xffffu << (lane & 16u)) {}
-    __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & 0xffffu; }
-    __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(gmask, v, (int)src, 16); }
-    __device__ __forceinline__ uint32_t match_any(uint32_t key) const { return (__match_any_sync(gmask, key) >> gshift) & 0xffffu; }
+    __device__ __forceinline__ explicit LaneGroup(uint32_t lane)
+        : sub(lane & (G - 1u)), gshift(lane & ~uint32_t(G - 1)), gmask(kAll << (lane & ~uint32_t(G - 1))) {}
+    __device__ __forceinline__ uint32_t ballot(bool p) const { return (__ballot_sync(gmask, p) >> gshift) & kAll; }
+    __device__ __forceinline__ uint32_t shfl(uint32_t v, uint32_t src) const { return __shfl_sync(gmask, v, (int)src, G); }
+    __device__ __forceinline__ uint32_t match_any(uint32_t key) const { return (__match_any_sync(gmask, key) >> gshift) & kAll; }
     __device__ __forceinline__ void sync() const { __syncwarp(gmask); }
 };
 
+template <int G>
 struct SeqProducerG {                            // SeqProducer for a lane group (all state uniform within the group)
     uint4 *q;
     volatile uint32_t *meta;
     uint64_t *bars;
     uint32_t k, qn, block, first;
-    HalfWarp g;
+    LaneGroup<G> g;
     __device__ __forceinline__ void flush(uint32_t last)
     {
         const uint32_t h = k & 1u;
@@ -931,10 +935,11 @@ struct SeqProducerG {                            // SeqProducer for a lane group
 // The search half of compress_internal (compress.rs:318-489) for one block on 16 lanes; u16 table in global memory.
 // Same scheme as match_block_view (speculative pre-batch candidates, shuffles / match.any for in-batch slot collisions,
 // commit of the executed probes), 16 probes per batch, 16 bytes per extension round.
+template <int kG>
 __device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src, uint32_t n, uint16_t *tab, bool cont, bool h5,
-                                                 SeqProducerG &pr, const HalfWarp &g)
+                                                 SeqProducerG<kG> &pr, const LaneGroup<kG> &g)
 {
-    constexpr uint32_t G = 16u, kInvalid = 0xffffu, kAll = 0xffffu;
+    constexpr uint32_t G = kG, kInvalid = 0xffffu, kAll = LaneGroup<kG>::kAll;
     const uint32_t sub = g.sub, lt_mask = (1u << sub) - 1u;
     if (n < 13) {                                               // compress.rs:343-346
         pr.push_final(0, n);
@@ -961,7 +966,7 @@ __device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src
     for (;;) {                                                  // one sequence per iteration
         uint32_t base = cur, nbatch = 0, cand, mpos;
         for (;;) {                                              // probe batches: compress.rs:373-439
-            const uint32_t stride = (nbatch >> 1) + 1u;         // 32 probes per step value = two batches of 16
+            const uint32_t stride = nbatch / (32u / G) + 1u;     // 32 probes per step value = 32/G batches
             const uint32_t p = base + sub * stride;
             const bool term = p > last_probe, live = !term;
             uint32_t v4, hi;
@@ -1047,7 +1052,7 @@ __device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src
                 mpos -= kb; cand -= kb;
             }
         }
-        if (kf == G) {                                          // long match: 64 bytes per round (compress.rs:156-216)
+        if (kf == G) {                                          // long match: 4 G bytes per round (compress.rs:156-216)
             for (;;) {
                 const uint32_t pos = end + 4u * sub;
                 const bool full = pos + 4u <= lim;              // this lane's word lies before n - END_OFFSET
@@ -1073,12 +1078,12 @@ __device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src
     }
 }
 
-// kM matcher warps (2 chains each) + kE emitter warps per CTA; 8 KiB u16 table per chain in global memory.
-template <int kM, int kE>
+// kM matcher warps (32/G chains each) + kE emitter warps per CTA; 8 KiB u16 table per chain in global memory.
+template <int G, int kM, int kE>
 __global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
-lz4_compress_blocks_gtab16(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
+lz4_compress_blocks_gtabg(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
 {
-    constexpr int kC = 2 * kM, kR = kC / kE;                   // chains per CTA, rings per emitter
+    constexpr int kC = (32 / G) * kM, kR = kC / kE;            // chains per CTA, rings per emitter
     static_assert(kC % kE == 0, "every emitter serves the same number of chains");
     __shared__ __align__(16) uint4 q_s[kC * 2 * kSeqBatchEntries];
     __shared__ uint32_t meta_s[kC * 8];
@@ -1093,9 +1098,9 @@ lz4_compress_blocks_gtab16(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
                             st_s + e * kR, lane);
         return;
     }
-    const HalfWarp g(lane);
-    const uint32_t chain = warp * 2u + (lane >> 4);
-    SeqProducerG pr{q_s + chain * 2 * kSeqBatchEntries, meta_s + chain * 8, bars_s + chain * 4, 0u, 0u, 0u, 0u, g};
+    const LaneGroup<G> g(lane);
+    const uint32_t chain = warp * (32u / G) + lane / G;
+    SeqProducerG<G> pr{q_s + chain * 2 * kSeqBatchEntries, meta_s + chain * 8, bars_s + chain * 4, 0u, 0u, 0u, 0u, g};
     uint16_t *tab = gtab + ((size_t)blockIdx.x * kC + chain) * 4096;
     for (;;) {
         uint32_t b = 0;
@@ -1111,7 +1116,7 @@ lz4_compress_blocks_gtab16(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         }
         const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
         pr.block = b; pr.first = 1;
-        match_block_half(a.in + a.in_off[b], n, tab, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, g);
+        match_block_half<G>(a.in + a.in_off[b], n, tab, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, g);
     }
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0);

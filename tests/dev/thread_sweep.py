@@ -71,15 +71,10 @@ if MODE == "thread":
     for lanes in (32, 16, 8):
         run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
 elif MODE == "g16":
-    run({}, "untagged gtab 7+1 x8 (round 1)")
-    run({"LZ4B200_L2_PERSIST_MB": "1000", "LZ4B200_DEBUG": "1"}, "gtab 7+1 x8, persisting L2 = max")
-    run({"LZ4B200_L2_PERSIST_MB": "64"}, "gtab 7+1 x8, persisting L2 = 64 MB")
-    run({"LZ4B200_L2_PERSIST_MB": "0"}, "gtab 7+1 x8, persisting L2 = 0")
-    for shape in ("62", "71"):
-        for ctas in (8, 6, 5, 4):
-            run({"LZ4B200_ENC_G16": shape, "LZ4B200_ENC_G16_CTAS": str(ctas)}, f"half-warp matchers {shape}, {ctas} CTAs/SM")
-    run({"LZ4B200_ENC_G16": "62", "LZ4B200_ENC_G16_CTAS": "6", "LZ4B200_L2_PERSIST_MB": "1000"}, "half-warp 62 x6 + persisting L2 max")
-    run({"LZ4B200_ENC_G16": "62", "LZ4B200_ENC_G16_CTAS": "4", "LZ4B200_L2_PERSIST_MB": "1000"}, "half-warp 62 x4 + persisting L2 max")
+    run({}, "gtab 7+1 x8 (round 1 default)")
+    for shape in ("71", "62", "871", "862"):
+        for ctas in (8, 6):
+            run({"LZ4B200_ENC_G16": shape, "LZ4B200_ENC_G16_CTAS": str(ctas)}, f"lane-group matchers {shape}, {ctas} CTAs/SM")
 else:
     run({"LZ4B200_ENC_GTAG": "0"}, "untagged gtab 7+1 x8 (round 1)")
     for ctas in (8, 7, 6, 5):

@@ -193,8 +193,9 @@ def test_tags_remove_the_false_candidate_fetches():
 
 
 @pytest.mark.parametrize("name,data", [c for c in CASES if len(c[1]) <= 65536], ids=[c[0] for c in CASES if len(c[1]) <= 65536])
-def test_half_warp_batches_keep_the_parse(name, data):
-    """lz4_compress_blocks_gtab16: 16 probes per batch, two batches per step value of compress.rs:374-378."""
-    assert warp_encode(data, G=16) == oracle.compress_block(data)
-    assert warp_encode(data, cont=True, h5=True, G=16) == oracle.compress_block_cont(data)
-    assert warp_encode(data, cont=False, h5=True, G=16) == oracle.compress_block_fresh_h5(data)
+def test_lane_group_batches_keep_the_parse(name, data):
+    """lz4_compress_blocks_gtabg<G>: G probes per batch, 32/G batches per step value of compress.rs:374-378."""
+    for G in (16, 8):
+        assert warp_encode(data, G=G) == oracle.compress_block(data)
+        assert warp_encode(data, cont=True, h5=True, G=G) == oracle.compress_block_cont(data)
+        assert warp_encode(data, cont=False, h5=True, G=G) == oracle.compress_block_fresh_h5(data)

@@ -26,6 +26,9 @@ VARIANTS = {
     "warp": {"LZ4B200_THREAD_MIN": "4000000000", "LZ4B200_ENC_SOLO": "0"},
     "warp_tagged": {"LZ4B200_ENC_GTAG": "71"},
     "warp_half": {"LZ4B200_ENC_G16": "62"},
+    "warp_half71": {"LZ4B200_ENC_G16": "71"},
+    "warp_quarter": {"LZ4B200_ENC_G16": "871"},
+    "warp_quarter62": {"LZ4B200_ENC_G16": "862", "LZ4B200_ENC_G16_CTAS": "6"},
 }
 
 
