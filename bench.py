@@ -151,23 +151,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def ncu_traffic(prefix: str):
-    """(kernel name, DRAM bytes per launch) of the first kernel whose name contains `prefix` in the committed
-    ncu --set full summary of this workload (profiles/r1_ncu_summary.json), or (prefix, None)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_summary.json")
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` — the name the launcher reported
+    for this run (lz4b200_ctx_last_kernel) — from the committed ncu --set full summaries of this workload
+    (profiles/r2_ncu_summary.json, then r1), or None when that exact kernel has no capture: a profile is never
+    attributed to a kernel it was not taken from."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    try:
-        for e in json.load(open(path)):
-            if prefix in e.get("kernel", ""):
-                tot = 0.0
-                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    v, u = e[k].split()
-                    tot += float(v) * unit[u]
-                name = e["kernel"].replace("void ", "").split("(")[0].replace("unsigned short", "u16").replace("(int)", "")
-                return name, tot
-    except Exception:                                           # noqa: BLE001
-        pass
-    return prefix, None
+    norm = lambda n: n.replace("void ", "").split("(")[0].replace("lz4b200::", "").replace("(int)", "").replace("false", "0").replace("true", "1").replace(" ", "")
+    for f in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+        try:
+            for e in json.load(open(os.path.join(ROOT, "profiles", f))):
+                if norm(e.get("kernel", "")) == norm(kernel):
+                    tot = 0.0
+                    for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                        v, u = e[k].split()
+                        tot += float(v) * unit[u]
+                    return tot, f
+        except Exception:                                       # noqa: BLE001
+            pass
+    return None, None
 
 
 def build_workload(nblocks: int, rank: int):
@@ -501,8 +503,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    k1_name, k1_traffic = ncu_traffic("lz4_compress_blocks")
-    k2_name, k2_traffic = ncu_traffic("lz4_decompress_blocks")
+    from lz4_flex_b200 import _native
+    k1_name = _native.lib().lz4b200_ctx_last_kernel(ctx.handle, 0).decode()
+    k2_name = _native.lib().lz4b200_ctx_last_kernel(ctx.handle, 1).decode()
+    k1_traffic, k1_src = ncu_traffic(k1_name)
+    k2_traffic, k2_src = ncu_traffic(k2_name)
     mib_rank = nb * BLOCK / 2**20
     ms_per_step = elapsed_ms / args.steps
     value = world * mib_rank / (ms_per_step / 1e3)
@@ -535,11 +540,13 @@ def run_ours(args):
         # the same workload (profiles/r1_ncu_summary.json; see ncu_traffic())
         "roofline": {"kernel": k1_name, "bound": "hbm", "achieved": ach_c, "peak": peak,
                      "unit": "GB/s", "frac": ach_c / peak, "traffic": k1_traffic if nb == NBLOCKS_DEFAULT else None,
+                     "traffic_source": f"profiles/{k1_src} (ncu --set full capture of this kernel on this workload)" if k1_src else None,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes},
         "roofline_decompress": {"kernel": k2_name, "bound": "hbm", "achieved": ach_d, "peak": peak,
                                 "unit": "GB/s", "frac": ach_d / peak,
-                                "traffic": k2_traffic if nb == NBLOCKS_DEFAULT else None, "peak_source": peak_src,
+                                "traffic": k2_traffic if nb == NBLOCKS_DEFAULT else None,
+                                "traffic_source": f"profiles/{k2_src}" if k2_src else None, "peak_source": peak_src,
                                 "algorithmic_bytes_per_launch": alg_bytes},
         "cpu_baseline": None if cpu_all is None else {
             "value": cpu_all["roundtrip_mibs"], "unit": "MiB/s", "cores": cores, "threads": threads, "kind": "port",
@@ -680,7 +687,7 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
             "collective": {"compress_kernel_ms": k_ms, "exchange_and_pack_ms": x_ms,
                            "how": "all_gather of 8-byte sizes, device prefix sum, pack kernel storing into rank 0's "
                                   "buffer over NVLink (CUDA IPC mapping), 4-byte all_reduce as completion; no host sync"},
-            "roofline": {"kernel": "lz4_compress_blocks_solo", "bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9,
+            "roofline": {"kernel": _last_kernel(ctx, 0), "bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
             "e2e": {"value": total / 2**20 / e2e_s, "unit": "MiB/s", "ms_per_step": 1e3 * e2e_s,
@@ -691,6 +698,11 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
         }
     g.close()
     return rec
+
+
+def _last_kernel(ctx, which: int) -> str:
+    from lz4_flex_b200 import _native
+    return _native.lib().lz4b200_ctx_last_kernel(ctx.handle, which).decode()
 
 
 def cpu_frame_baseline(nblocks: int):

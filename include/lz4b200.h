@@ -100,6 +100,9 @@ void lz4b200_ctx_destroy(lz4b200_ctx *ctx);
 void lz4b200_ctx_set_priority(lz4b200_ctx *ctx, int high);
 /* The context's own stream (cudaStream_t). */
 void *lz4b200_ctx_stream(lz4b200_ctx *ctx);
+/* Name of the kernel the launcher picked for the context's last compress (which = 0) / decompress (which = 1) batch —
+ * diagnostics only: bench.py records it beside the roofline so a profile is never attributed to the wrong kernel. */
+const char *lz4b200_ctx_last_kernel(const lz4b200_ctx *ctx, int which);
 
 /* ---- sizes ------------------------------------------------------------------------------ */
 

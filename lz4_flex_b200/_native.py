@@ -110,6 +110,7 @@ SIGNATURES = {
     "lz4b200_ctx_destroy": (None, [_vp]),
     "lz4b200_ctx_set_priority": (None, [_vp, _i32]),
     "lz4b200_ctx_stream": (_vp, [_vp]),
+    "lz4b200_ctx_last_kernel": (C.c_char_p, [_vp, _i32]),
     "lz4b200_max_output_size": (_sz, [_sz]),
     "lz4b200_compress_into": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "lz4b200_compress_prepend_size": (_i32, [_vp, _vp, _sz, _vp, _sz, _psz]),

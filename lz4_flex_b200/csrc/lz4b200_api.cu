@@ -287,6 +287,7 @@ struct lz4b200_ctx {
     uint32_t enc_thread_max = 16384, dec_thread_max = 65536;
 #endif
     std::string last_error;
+    const char *last_kernel[2] = {"", ""};   // what the launchers picked last: [0] compress, [1] decompress (for the bench record)
     uint32_t range_nb = 0;                    // lz4b200_frame_range_compress -> _pack hand-over
     const uint8_t *range_in = nullptr;
     size_t frame_budget = 256u << 20;         // device bytes the frame decoder's block slots / staged input may take per group
@@ -342,6 +343,7 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
 #endif
     if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     else lz4_decompress_blocks<G, 0, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    ctx->last_kernel[1] = G == 8 ? "lz4_decompress_blocks<8, 0, 0>" : G == 16 ? "lz4_decompress_blocks<16, 0, 0>" : "lz4_decompress_blocks<32, 0, 0>";
     CTX_CUDA(ctx, cudaGetLastError());
     return LZ4B200_OK;
 }
@@ -506,6 +508,7 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     if (!a.dict_len && ctx->enc_solo == 2 && max_in_len != 0 && (max_in_len > 65536u || a.nblocks <= ctx->enc_solo_small_max)) {
         const uint32_t grid = std::min<uint32_t>(a.nblocks, (uint32_t)(ctx->sm_count * ctx->enc_solo2_ctas_per_sm));
         lz4_compress_blocks_solo2<<<grid, 64, kSolo2SmemBytes, s>>>(a, tickets + 4);
+        ctx->last_kernel[0] = "lz4_compress_blocks_solo2";
         CTX_CUDA(ctx, cudaGetLastError());
         return LZ4B200_OK;
     }
@@ -518,15 +521,17 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
                 const int m = (ctx->enc_g16 % 100) / 10, gsz = ctx->enc_g16 >= 800 ? 8 : 16;   // 62 | 71 (G = 16), 862 | 871 (G = 8)
                 const int per_cta = (32 / gsz) * m;
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
-                if (gsz == 8 && m == 7) lz4_compress_blocks_gtabg<8, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-                else if (gsz == 8) lz4_compress_blocks_gtabg<8, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-                else if (m == 7) lz4_compress_blocks_gtabg<16, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-                else lz4_compress_blocks_gtabg<16, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                if (gsz == 8 && m == 7) { lz4_compress_blocks_gtabg<8, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtabg<8, 7, 1>"; }
+                else if (gsz == 8) { lz4_compress_blocks_gtabg<8, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtabg<8, 6, 2>"; }
+                else if (m == 7) { lz4_compress_blocks_gtabg<16, 7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtabg<16, 7, 1>"; }
+                else { lz4_compress_blocks_gtabg<16, 6, 2><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtabg<16, 6, 2>"; }
             } else {
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * 8u);
                 lz4_compress_blocks_gtab<uint16_t, 7, 1, 0><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                ctx->last_kernel[0] = "lz4_compress_blocks_gtab<unsigned short, 7, 1, 0>";
             }
         } else {
+            ctx->last_kernel[0] = "lz4_compress_blocks_split<unsigned short, 3, 0>";
             const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc16Pairs - 1) / kEnc16Pairs, (uint32_t)(ctx->sm_count * ctx->enc16s_ctas_per_sm));
             if (a.dict_len)
                 lz4_compress_blocks_split<uint16_t, kEnc16Pairs, true>
@@ -538,6 +543,7 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         CTX_CUDA(ctx, cudaGetLastError());
     }
     if (max_in_len == 0 || (uint64_t)max_in_len + a.dict_len > 65536u) {
+        if (max_in_len > 65536u) ctx->last_kernel[0] = "lz4_compress_blocks_split<unsigned int, 2, 0>";
         const uint32_t grid = std::min<uint32_t>((a.nblocks + kEnc32Pairs - 1) / kEnc32Pairs, (uint32_t)(ctx->sm_count * ctx->enc32s_ctas_per_sm));
         if (a.dict_len)
             lz4_compress_blocks_split<uint32_t, kEnc32Pairs, true>
@@ -716,6 +722,11 @@ void lz4b200_ctx_set_priority(lz4b200_ctx *ctx, int high)
 }
 
 void *lz4b200_ctx_stream(lz4b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+const char *lz4b200_ctx_last_kernel(const lz4b200_ctx *ctx, int which)
+{
+    return ctx && (which == 0 || which == 1) ? ctx->last_kernel[which] : "";
+}
 
 size_t lz4b200_max_output_size(size_t n) { return 16 + 4 + (size_t)((uint64_t)n * 110 / 100); }
 
