@@ -621,7 +621,7 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
     pb = 6
     base = 508
     small = hdfs_range((base + rank * pb) * bs, pb * bs)
-    g = sharded.PeerFrameGather(world * pb * bs, 7, rank, world, ctx, base_block=base)
+    g = sharded.make_frame_gather(world * pb * bs, 7, rank, world, ctx, base_block=base)
     g.step(torch.from_numpy(small).to(dev))
     torch.cuda.synchronize()
     parity = None
@@ -634,7 +634,7 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
     g.close()
 
     # ---- the timed workload ------------------------------------------------------------------------------------------
-    g = sharded.PeerFrameGather(total, 7, rank, world, ctx)
+    g = sharded.make_frame_gather(total, 7, rank, world, ctx)
     for _ in range(max(args.warmup, 3)):
         g.step(d_in)
     torch.cuda.synchronize()
@@ -663,7 +663,7 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
         d_in.copy_(h_in, non_blocking=True)
         g.step(d_in)
         if rank == 0:
-            h_frame.copy_(g.frame[:frame_len], non_blocking=True)
+            h_frame.copy_(g.result()[:frame_len], non_blocking=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -685,8 +685,7 @@ def measure_sharded_frame(args, ctx, dev, rank, world, numa_info=None):
             "value": total / 2**20 / (ms / 1e3), "unit": "MiB/s", "ms_per_step": ms, "steps": steps,
             "scaling": "weak", "frame_bytes": frame_len, "ratio": frame_len / total,
             "collective": {"compress_kernel_ms": k_ms, "exchange_and_pack_ms": x_ms,
-                           "how": "all_gather of 8-byte sizes, device prefix sum, pack kernel storing into rank 0's "
-                                  "buffer over NVLink (CUDA IPC mapping), 4-byte all_reduce as completion; no host sync"},
+                           "how": "all_gather of the 8-byte packed sizes, then: " + g.transport},
             "roofline": {"kernel": _last_kernel(ctx, 0), "bound": "hbm", "achieved": alg / (k_ms / 1e3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},

@@ -108,6 +108,10 @@ def frame_compress_sharded(local, total_len: int, block_size_id: int, rank: int,
     return gather_frame(part, part_len, info, rank, world, group)
 
 
+class PeerMappingUnavailable(RuntimeError):
+    """Raised on EVERY rank when the frame buffer cannot be shared over CUDA IPC; callers fall back to StagedFrameGather."""
+
+
 class _DevPtr:
     """A raw device allocation as something torch.as_tensor understands (__cuda_array_interface__)."""
 
@@ -121,6 +125,8 @@ class PeerFrameGather:
     Every rank calls step(d_in) with its byte range resident on its GPU; after the step rank 0 holds the frame in
     `self.frame` (uint8 CUDA tensor view of the shared buffer) and its length in `self.frame_len` (0-d int64 CUDA
     tensor).  Nothing in step() synchronises with the host."""
+
+    transport = "pack kernel stores into rank 0's buffer over NVLink (CUDA IPC mapping); no host sync"
 
     def __init__(self, total_len: int, block_size_id: int, rank: int, world: int, ctx, group=None, base_block: int = 0):
         import ctypes as C
@@ -146,20 +152,36 @@ class PeerFrameGather:
         handle = (C.c_uint8 * 64)()
         p = C.c_void_p()
         self._owned = self._mapped = None
+        # Every rank must reach the same verdict about the mapping, whatever fails where: rank 0 broadcasts its handle
+        # (or None), the others try to map it, and a MIN all_reduce of the outcome decides for all.
+        box = [None]
         if rank == 0:
-            st = self.L.lz4b200_peer_alloc(ctx.handle, cap, C.byref(p), handle)
-            if st != 0:
-                raise RuntimeError("lz4b200_peer_alloc failed: " + ctx.last_cuda_error())
-            self._owned = p.value
+            if self.L.lz4b200_peer_alloc(ctx.handle, cap, C.byref(p), handle) == 0:
+                self._owned = p.value
+                box = [bytes(handle)]
+        ok = 1
         if world > 1:
-            box = [bytes(handle) if rank == 0 else None]
             dist.broadcast_object_list(box, src=0, group=group)
-            if rank != 0:
+            if box[0] is None:
+                ok = 0
+            elif rank != 0:
                 h = (C.c_uint8 * 64).from_buffer_copy(box[0])
-                st = self.L.lz4b200_peer_open(ctx.handle, h, C.byref(p))
-                if st != 0:
-                    raise RuntimeError("lz4b200_peer_open failed: " + ctx.last_cuda_error())
-                self._mapped = p.value
+                if self.L.lz4b200_peer_open(ctx.handle, h, C.byref(p)) == 0:
+                    self._mapped = p.value
+                else:
+                    ok = 0
+            t = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", ctx.device))
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            ok = int(t.item())
+        elif box[0] is None:
+            ok = 0
+        if not ok:
+            if self._mapped:
+                self.L.lz4b200_peer_close(ctx.handle, self._mapped)
+            if self._owned:
+                self.L.lz4b200_peer_free(ctx.handle, self._owned)
+            self._owned = self._mapped = None
+            raise PeerMappingUnavailable("CUDA IPC mapping of rank 0's frame buffer failed: " + ctx.last_cuda_error())
         self.frame_ptr = p.value
         self.d_total = torch.zeros(1, dtype=torch.int64, device=dev)
         self.d_all = torch.zeros(world, dtype=torch.int64, device=dev)
@@ -229,3 +251,54 @@ class PeerFrameGather:
             self.frame = None
             self.L.lz4b200_peer_free(self.ctx.handle, self._owned)
             self._owned = None
+
+
+class StagedFrameGather:
+    """Same interface as PeerFrameGather with the backend-neutral exchange (all_gather of sizes + send/recv of the packed
+    chunks, gather_frame): the fallback when the peer mapping is unavailable.  Synchronises with the host once per step."""
+
+    transport = "nccl send/recv of packed chunks (host-synchronised sizes)"
+
+    def __init__(self, total_len: int, block_size_id: int, rank: int, world: int, ctx, group=None, base_block: int = 0):
+        import torch
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.info = FrameInfo(block_size=BlockSize(block_size_id))
+        self.bs = self.info.block_size.get_size()
+        nblocks = -(-total_len // self.bs)
+        self.first_block = base_block + block_range(nblocks, rank, world)[0]
+        self.frame = None
+        self.frame_len = torch.zeros((), dtype=torch.int64)
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(self, d_in, timed: bool = False):
+        import torch
+        if timed:
+            self.ev[0].record()
+        part, d_total = compress_range_device(d_in, self.bs, self.first_block, self.ctx)
+        if timed:
+            self.ev[1].record()
+        self.frame = gather_frame(part, int(d_total.item()), self.info, self.rank, self.world, self.group)
+        if self.rank == 0:
+            self.frame_len = torch.tensor(self.frame.numel(), dtype=torch.int64)
+        if timed:
+            self.ev[2].record()
+
+    def timings_ms(self):
+        return self.ev[0].elapsed_time(self.ev[1]), self.ev[1].elapsed_time(self.ev[2])
+
+    def result(self):
+        return self.frame if self.rank == 0 else None
+
+    def close(self):
+        self.frame = None
+
+
+def make_frame_gather(total_len: int, block_size_id: int, rank: int, world: int, ctx, group=None, base_block: int = 0):
+    """PeerFrameGather when the ranks can share rank 0's frame buffer, StagedFrameGather otherwise (same verdict on every rank)."""
+    import os
+    if os.environ.get("LZ4B200_SHARDED_STAGED") != "1":
+        try:
+            return PeerFrameGather(total_len, block_size_id, rank, world, ctx, group, base_block)
+        except PeerMappingUnavailable:
+            pass
+    return StagedFrameGather(total_len, block_size_id, rank, world, ctx, group, base_block)
