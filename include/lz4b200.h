@@ -170,7 +170,9 @@ lz4b200_status lz4b200_decompress_batch_device(lz4b200_ctx *ctx,
  * Host arrays; includes H2D of inputs and D2H of results (pinned host memory gives full
  * PCIe speed, pageable memory works).  Compressed blocks come back PACKED: block b is
  * written at out + out_off[b] where out_off[] is an OUTPUT (out_off[b+1] = out_off[b] +
- * out_len[b]), so only the produced bytes cross PCIe; `out_cap_total` bounds the sum. */
+ * out_len[b]), so only the produced bytes cross PCIe; `out_cap_total` bounds the sum.
+ * Decompress: bytes of an output slot past the block's decoded length are overwritten with zeros (the reference
+ * leaves them unspecified: wild copies); nothing of an earlier call can appear there. */
 lz4b200_status lz4b200_compress_batch_host(lz4b200_ctx *ctx,
     const uint8_t *in, const uint64_t *in_off, const uint32_t *in_len, const uint8_t *flags,
     uint8_t *out, size_t out_cap_total, uint64_t *out_off,

@@ -1136,6 +1136,9 @@ static lz4b200_status decompress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t
         CTX_CUDA(ctx, ln.out.reserve(c.b - c.a + 16));
         CTX_CUDA(ctx, cudaStreamWaitEvent(ln.stream, pl.desc_ready, 0));
         CTX_CUDA(ctx, cudaMemcpyAsync(ln.in.p, in + c.in_lo, c.in_hi - c.in_lo, cudaMemcpyHostToDevice, ln.stream));
+        // The whole capacity region of every slot travels back (the decoded sizes are only known after the kernel), so
+        // what lies past a block's decoded length must not be whatever an earlier call left in this staging buffer.
+        CTX_CUDA(ctx, cudaMemsetAsync(ln.out.p, 0, c.b - c.a, ln.stream));
         BatchArgs a{ln.in.p, ctx->d_in_off.p + c.b0, ctx->d_in_len.p + c.b0, nullptr, ln.out.p, ctx->d_out_off.p + c.b0,
                     ctx->d_out_cap.p + c.b0, ctx->d_out_len.p + c.b0, ctx->d_status.p + c.b0, ctx->d_expected.p + c.b0, n,
                     nullptr};
