@@ -26,6 +26,9 @@
 #ifndef DEC_DEFER8
 #define DEC_DEFER8 0     // 1: deferred match stores cover 8 byte steps (64 bytes for G=8) instead of 4 (A/B aid)
 #endif
+#ifndef DEC_DEFER2
+#define DEC_DEFER2 0     // 1: TWO short matches in flight (the older one is stored when a third arrives); build-time A/B
+#endif
 #ifndef DEC_VARIANT_A
 #define DEC_VARIANT_A 1
 #endif
@@ -382,6 +385,23 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     uint8_t pv4 = 0, pv5 = 0, pv6 = 0, pv7 = 0;
 #endif
     uint32_t p_at = 0, p_len = 0;                              // pending match: output position, length (0 = none)
+#if DEC_DEFER2
+    uint8_t qv0 = 0, qv1 = 0, qv2 = 0, qv3 = 0;                // the OLDER pending match (two in flight)
+    uint32_t q_at = 0, q_len = 0;
+#define FLUSH_OLDER()                                                          \
+    do {                                                                       \
+        if (q_len) {                                                           \
+            uint8_t *qd = dst + q_at;                                          \
+            if (sub < q_len) qd[sub] = qv0;                                    \
+            if (sub + G < q_len) qd[sub + G] = qv1;                            \
+            if (sub + 2 * G < q_len) qd[sub + 2 * G] = qv2;                    \
+            if (sub + 3 * G < q_len) qd[sub + 3 * G] = qv3;                    \
+            q_len = 0;                                                         \
+        }                                                                      \
+    } while (0)
+#else
+#define FLUSH_OLDER() do { } while (0)
+#endif
 #if DEC_DEFER8
 #define FLUSH_PENDING_HI()                                                     \
             if (sub + 4 * G < p_len) pd[sub + 4 * G] = pv4;                    \
@@ -393,6 +413,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
 #endif
 #define FLUSH_PENDING()                                                        \
     do {                                                                       \
+        FLUSH_OLDER();                                                         \
         if (kDefer && p_len) {                                                           \
             uint8_t *pd = dst + p_at;                                          \
             if (sub < p_len) pd[sub] = pv0;                                    \
@@ -447,7 +468,19 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
                         ip = q + adv;
                         continue;
                     }
+#if DEC_DEFER2
+                    // two in flight: a new short match whose source ends below the oldest unstored byte only retires the
+                    // OLDER pending match (its loads were issued two sequences ago); anything else drains both
+                    if (kDefer && dist >= mlen && mlen <= 4u * G && p_len &&
+                        op - dist + mlen <= (q_len ? q_at : p_at)) {
+                        FLUSH_OLDER();
+                        qv0 = pv0; qv1 = pv1; qv2 = pv2; qv3 = pv3; q_at = p_at; q_len = p_len; p_len = 0;
+                    } else {
+                        FLUSH_PENDING();
+                    }
+#else
                     FLUSH_PENDING();
+#endif
                     __syncwarp(gmask);
                     if (kDefer && dist >= mlen && mlen <= (DEC_DEFER8 ? 8u : 4u) * G) {
                         const uint8_t *from = dst + op - dist;
@@ -479,6 +512,7 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     FLUSH_PENDING();
 #undef FLUSH_PENDING
 #undef FLUSH_PENDING_HI
+#undef FLUSH_OLDER
     r.written = op;
     return r;
 }

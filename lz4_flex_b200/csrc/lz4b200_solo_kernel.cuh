@@ -56,12 +56,12 @@ constexpr size_t kSoloSmemBytes = kSoloRing + 4096 * 4 + 2 * kSeqBatchEntries * 
 __global__ void __launch_bounds__(64)
 lz4_compress_blocks_solo(BatchArgs a, uint32_t *tickets)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t *ring = smem_raw;
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + kSoloRing);
-    uint4 *q = reinterpret_cast<uint4 *>(smem_raw + kSoloRing + 16384);
-    uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + kSoloRing + 16384 + 2 * kSeqBatchEntries * 16);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kSoloRing + 16384 + 2 * kSeqBatchEntries * 16 + 32);
+    extern __shared__ __align__(128) uint8_t solo_smem[];
+    uint8_t *ring = solo_smem;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(solo_smem + kSoloRing);
+    uint4 *q = reinterpret_cast<uint4 *>(solo_smem + kSoloRing + 16384);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(solo_smem + kSoloRing + 16384 + 2 * kSeqBatchEntries * 16);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(solo_smem + kSoloRing + 16384 + 2 * kSeqBatchEntries * 16 + 32);
     uint64_t *rbars = bars + 4;
     if (threadIdx.x < 4u + kSoloSlots) mbar_init(bars + threadIdx.x, 1u);
     __syncthreads();
@@ -230,12 +230,12 @@ constexpr size_t kSolo2SmemBytes = kRing2Bytes + 4096 * 4 + 2 * kSeqBatchEntries
 __global__ void __launch_bounds__(64)
 lz4_compress_blocks_solo2(BatchArgs a, uint32_t *tickets)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t *ring = smem_raw;
-    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + kRing2Bytes);
-    uint4 *q = reinterpret_cast<uint4 *>(smem_raw + kRing2Bytes + 16384);
-    uint32_t *meta = reinterpret_cast<uint32_t *>(smem_raw + kRing2Bytes + 16384 + 2 * kSeqBatchEntries * 16);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kRing2Bytes + 16384 + 2 * kSeqBatchEntries * 16 + 32);
+    extern __shared__ __align__(128) uint8_t solo_smem[];
+    uint8_t *ring = solo_smem;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(solo_smem + kRing2Bytes);
+    uint4 *q = reinterpret_cast<uint4 *>(solo_smem + kRing2Bytes + 16384);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(solo_smem + kRing2Bytes + 16384 + 2 * kSeqBatchEntries * 16);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(solo_smem + kRing2Bytes + 16384 + 2 * kSeqBatchEntries * 16 + 32);
     uint64_t *rbars = bars + 4;
     if (threadIdx.x < 4u + kRing2Slots) mbar_init(bars + threadIdx.x, 1u);
     __syncthreads();

@@ -66,15 +66,17 @@ def run(env, label, iters=5):
     ctx.close()
 
 MODE = sys.argv[3] if len(sys.argv) > 3 else "gtag"
-if MODE == "thread":
+if MODE == "plain":
+    run({}, "default launch policy of " + os.path.basename(os.environ["LZ4B200_SO_OVERRIDE"]))
+elif MODE == "thread":
     run({"LZ4B200_THREAD_MIN": "4000000000"}, "round-1 warp kernels (gtab / G=8)")
     for lanes in (32, 16, 8):
         run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
 elif MODE == "g16":
     run({}, "gtab 7+1 x8 (round 1 default)")
-    for shape in ("71", "62", "871", "862"):
-        for ctas in (8, 6):
-            run({"LZ4B200_ENC_G16": shape, "LZ4B200_ENC_G16_CTAS": str(ctas)}, f"lane-group matchers {shape}, {ctas} CTAs/SM")
+    for shape, ctas_list in (("71", (8, 6, 4)), ("871", (8, 6, 4, 3, 2)), ("862", (8, 4, 3)), ("62", (8,))):
+        for ctas in ctas_list:
+            run({"LZ4B200_ENC_G16": shape, "LZ4B200_ENC_G16_CTAS": str(ctas)}, f"lane-group matchers {shape}, {ctas} CTAs/SM", iters=4)
 else:
     run({"LZ4B200_ENC_GTAG": "0"}, "untagged gtab 7+1 x8 (round 1)")
     for ctas in (8, 7, 6, 5):
