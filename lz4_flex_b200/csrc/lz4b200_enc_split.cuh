@@ -1026,50 +1026,48 @@ __device__ __forceinline__ void match_block_half(const uint8_t *__restrict__ src
             nbatch++;
         }
         const uint32_t dist = mpos - cand;
-        // ---- extension: the first forward round (16 bytes) and the backward round share one memory round trip
+        // ---- extension (compress.rs:156-216, :272-287): forward in 4-byte words per lane (4 G bytes per round: a group of 8
+        // lanes covers 32 bytes, what the 32-lane matcher covers with bytes), backward in bytes; the first forward round and
+        // the backward round share one memory round trip
         const uint32_t room = min(cand, mpos - anchor);
-        const uint32_t qf = mpos + 4u + sub;
-        const bool inf = qf < lim;
-        const uint8_t f1 = view.byte(inf ? qf : mpos), f2 = view.byte((inf ? qf : mpos) - dist);
+        const bool inb = sub < room;
+        uint8_t b1 = 0, b2 = 1;
+        if (room) { b1 = view.byte(mpos - (inb ? 1u + sub : 0u)); b2 = view.byte(cand - (inb ? 1u + sub : 0u)); }
+        uint32_t end = mpos + 4u;
+        bool lim_stop;
+        for (;;) {
+            const uint32_t pos = end + 4u * sub;
+            const bool full = pos + 4u <= lim;                  // this lane's word lies before n - END_OFFSET
+            const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
+            const uint32_t nm = full ? (x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u) : 0u;
+            const uint32_t bad = g.ballot(nm < 4u);
+            if (bad) {
+                const uint32_t fl = (uint32_t)__ffs(bad) - 1u;
+                end += 4u * fl + g.shfl(nm, fl);
+                lim_stop = g.shfl(full ? 0u : 1u, fl) != 0u;    // stopped by the limit, not by a differing byte
+                break;
+            }
+            end += 4u * G;
+        }
         uint32_t kb = 0;
-        if (room) {                                             // compress.rs:272-287
-            const bool inb = sub < room;
-            const uint8_t b1 = view.byte(mpos - (inb ? 1u + sub : 0u)), b2 = view.byte(cand - (inb ? 1u + sub : 0u));
+        if (room) {
             const uint32_t bad = ~g.ballot(inb && b1 == b2) & kAll;
             kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
         }
-        const uint32_t badf = ~g.ballot(inf && f1 == f2) & kAll;
-        const uint32_t kf = badf ? (uint32_t)__ffs(badf) - 1u : G;
-        uint32_t end = mpos + 4u + kf;
+        if (lim_stop && end < lim) {                            // a word that crossed n - 6: at most 3 more bytes
+            const uint32_t q = end + sub;
+            const bool ok = sub < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
+            end += (uint32_t)__ffs(~g.ballot(ok) & kAll) - 1u;
+        }
         if (kb) {
             mpos -= kb; cand -= kb;
-            while (kb == G) {                                   // more than 16 bytes backwards: rare
+            while (kb == G) {                                   // more than G bytes backwards: rare
                 const uint32_t room2 = min(cand, mpos - anchor);
-                const bool inb = sub < room2;
-                const uint8_t b1 = view.byte(mpos - (inb ? 1u + sub : 0u)), b2 = view.byte(cand - (inb ? 1u + sub : 0u));
-                const uint32_t bad = ~g.ballot(inb && b1 == b2) & kAll;
+                const bool inb2 = sub < room2;
+                const uint8_t c1 = view.byte(mpos - (inb2 ? 1u + sub : 0u)), c2 = view.byte(cand - (inb2 ? 1u + sub : 0u));
+                const uint32_t bad = ~g.ballot(inb2 && c1 == c2) & kAll;
                 kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
                 mpos -= kb; cand -= kb;
-            }
-        }
-        if (kf == G) {                                          // long match: 4 G bytes per round (compress.rs:156-216)
-            for (;;) {
-                const uint32_t pos = end + 4u * sub;
-                const bool full = pos + 4u <= lim;              // this lane's word lies before n - END_OFFSET
-                const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
-                const uint32_t nm = full ? (x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u) : 0u;
-                const uint32_t bad = g.ballot(nm < 4u);
-                if (bad) {
-                    const uint32_t fl = (uint32_t)__ffs(bad) - 1u;
-                    end += 4u * fl + g.shfl(nm, fl);
-                    break;
-                }
-                end += 4u * G;
-            }
-            if (end < lim) {                                    // a word that crossed n - 6: at most 3 more bytes
-                const uint32_t q = end + sub;
-                const bool ok = sub < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
-                end += (uint32_t)__ffs(~g.ballot(ok) & kAll) - 1u;
             }
         }
         pr.push(anchor, mpos, dist, end);

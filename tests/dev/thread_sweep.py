@@ -74,7 +74,7 @@ elif MODE == "thread":
         run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
 elif MODE == "g16":
     run({}, "gtab 7+1 x8 (round 1 default)")
-    for shape, ctas_list in (("71", (8, 6, 4)), ("871", (8, 6, 4, 3, 2)), ("862", (8, 4, 3)), ("62", (8,))):
+    for shape, ctas_list in (("71", (8, 4)), ("871", (8, 4, 2)), ("862", (8,))):
         for ctas in ctas_list:
             run({"LZ4B200_ENC_G16": shape, "LZ4B200_ENC_G16_CTAS": str(ctas)}, f"lane-group matchers {shape}, {ctas} CTAs/SM", iters=4)
 else:
