@@ -514,7 +514,10 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
     }
     {                                                       // u16 tables: every block with input (+ dictionary) <= 64 KiB
         if (!a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
-            const size_t region = (size_t)ctx->sm_count * 8u * 28u * 4096u;            // u16 entries: 8 CTAs x up to 28 chains
+            // u16 entries: CTAs per SM x chains per CTA tables of 4096, one region per concurrently running launch
+            const int g16_m = (ctx->enc_g16 % 100) / 10, g16_g = ctx->enc_g16 >= 800 ? 8 : 16;
+            const size_t chains_per_sm = ctx->enc_g16 ? (size_t)ctx->enc_g16_ctas * (32 / g16_g) * g16_m : 8u * 7u;
+            const size_t region = (size_t)ctx->sm_count * chains_per_sm * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
             if (ctx->enc_g16) {                                                      // 2 or 4 chains per matcher warp
