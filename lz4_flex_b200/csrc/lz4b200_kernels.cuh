@@ -26,6 +26,9 @@
 #ifndef DEC_DEFER8
 #define DEC_DEFER8 0     // 1: deferred match stores cover 8 byte steps (64 bytes for G=8) instead of 4 (A/B aid)
 #endif
+#ifndef DEC_PREFETCH
+#define DEC_PREFETCH 0   // > 0: K2 prefetches the compressed stream this many bytes ahead of the token cursor into L1 (build-time A/B)
+#endif
 #ifndef DEC_DEFER2
 #define DEC_DEFER2 0     // 1: TWO short matches in flight (the older one is stored when a third arrives); build-time A/B
 #endif
@@ -145,6 +148,11 @@ struct WordView {
 // Semantics = the checked path of decompress_internal (decompress.rs:330-444): same bytes, same
 // first error, same OutputTooSmall{expected, actual} fields.
 // =============================================================================================
+__device__ __forceinline__ void prefetch_global_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 struct DecResult {
     uint32_t written;
     int32_t status;
@@ -426,6 +434,10 @@ __device__ __forceinline__ DecResult decode_block_simple(const uint8_t *__restri
     } while (0)
     for (;;) {
         if (ip + 8 <= n) {
+#if DEC_PREFETCH
+            // the token walk reads ~5 bytes per sequence: without a prefetch every eighth sequence waits for HBM on its token
+            if (sub == 0) prefetch_global_l1(src + min(ip + (uint32_t)DEC_PREFETCH, n - 1u));
+#endif
             const uint32_t v0 = view.ro4(ip);                  // token + (if no literals) offset + ext byte
             const uint32_t lit = (v0 >> 4) & 15u;
             const uint32_t q = ip + 1 + lit;                   // position of the offset
