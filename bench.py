@@ -216,18 +216,22 @@ def cpu_arm(data: np.ndarray, nblocks: int, threads: int, repeats: int):
     lens = np.full(nblocks, BLOCK, dtype=np.uint32)
     soff = np.arange(nblocks, dtype=np.uint64) * slot
     scap = np.full(nblocks, slot, dtype=np.uint32)
-    key = ("bufs", nblocks)
+    key = ("bufs", nblocks, threads)
     if key not in _POOLS:
-        comp = np.zeros(nblocks * slot, dtype=np.uint8)
-        back = np.zeros(nblocks * BLOCK, dtype=np.uint8)
-        comp[::4096] = 1; back[::4096] = 1                   # pre-fault
-        _POOLS[key] = (comp, back)
-    comp, back = _POOLS[key]
+        # every buffer the workers stream through is first touched BY the workers (pool.copy), so its pages spread over the
+        # host's NUMA nodes instead of all sitting on the node of this thread (measured: 9.5 vs 35 GiB/s decompress)
+        comp = np.empty(nblocks * slot, dtype=np.uint8)
+        back = np.empty(nblocks * BLOCK, dtype=np.uint8)
+        src = np.empty(nblocks * BLOCK, dtype=np.uint8)
+        pool.copy(comp); pool.copy(back); pool.copy(src, data[: nblocks * BLOCK])
+        _POOLS[key] = (comp, back, src)
+        pool.compress(src, offs, lens, comp, soff, scap)         # untimed warm-up pass
+    comp, back, src = _POOLS[key]
     best = (1e30, 1e30)
     clen = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        clen, st = pool.compress(data, offs, lens, comp, soff, scap)
+        clen, st = pool.compress(src, offs, lens, comp, soff, scap)
         t1 = time.perf_counter()
         olen, st2 = pool.decompress(comp, soff, clen, back, offs, lens)
         t2 = time.perf_counter()
@@ -387,6 +391,7 @@ def run_ours(args):
         step(evs[k])
     t_end.record()
     torch.cuda.synchronize()
+    k1_name, k2_name = _last_kernel(ctx, 0), _last_kernel(ctx, 1)       # what the launcher picked for the timed batches
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -503,9 +508,6 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    from lz4_flex_b200 import _native
-    k1_name = _native.lib().lz4b200_ctx_last_kernel(ctx.handle, 0).decode()
-    k2_name = _native.lib().lz4b200_ctx_last_kernel(ctx.handle, 1).decode()
     k1_traffic, k1_src = ncu_traffic(k1_name)
     k2_traffic, k2_src = ncu_traffic(k2_name)
     mib_rank = nb * BLOCK / 2**20

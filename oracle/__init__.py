@@ -98,6 +98,8 @@ def lib():
         L.lz4cpu_pool_create.argtypes = [C.c_int]
         L.lz4cpu_pool_destroy.restype = None
         L.lz4cpu_pool_destroy.argtypes = [C.c_void_p]
+        L.lz4cpu_pool_copy.restype = None
+        L.lz4cpu_pool_copy.argtypes = [C.c_void_p, u8p, u8p, sz]
         L.lz4cpu_pool_run.restype = None
         L.lz4cpu_pool_run.argtypes = [C.c_void_p, C.c_int] + [u8p] * 8 + [sz]
         _lib = L
@@ -298,6 +300,10 @@ class Pool:
         lib().lz4cpu_pool_run(self._h, decode, src.ctypes.data, in_off.ctypes.data, in_len.ctypes.data, dst.ctypes.data,
                               out_off.ctypes.data, out_cap.ctypes.data, out_len.ctypes.data, status.ctypes.data, nb)
         return out_len, status
+
+    def copy(self, dst, src=None):
+        """dst[:] = src (or zeros) with the pool's threads doing the first touch of dst's pages."""
+        lib().lz4cpu_pool_copy(self._h, dst.ctypes.data, src.ctypes.data if src is not None else None, dst.size)
 
     def compress(self, src, in_off, in_len, dst, out_off, out_cap):
         return self._run(0, src, in_off, in_len, dst, out_off, out_cap)

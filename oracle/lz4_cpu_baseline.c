@@ -201,7 +201,8 @@ struct lz4cpu_pool {
     uint64_t generation;
     int running, stop;
     /* the job */
-    int decode;
+    int decode;                 /* 0 compress, 1 decompress, 2 copy (first touch of a buffer by the workers) */
+    uint8_t *cp_dst; const uint8_t *cp_src; size_t cp_bytes;
     const uint8_t *in; const uint64_t *in_off; const uint32_t *in_len;
     uint8_t *out; const uint64_t *out_off; const uint32_t *out_cap; uint32_t *out_len; int32_t *status;
     size_t nblocks;
@@ -210,8 +211,20 @@ struct lz4cpu_pool {
 
 #define POOL_CHUNK 8
 
+#define COPY_PIECE ((size_t)1 << 20)
+
 static void pool_work(lz4cpu_pool *p, uint32_t *tab)
 {
+    if (p->decode == 2) {                                   /* parallel copy: pages land on the nodes of the threads that use them */
+        for (;;) {
+            const size_t i = atomic_fetch_add_explicit(&p->next, 1, memory_order_relaxed);
+            if (i * COPY_PIECE >= p->cp_bytes) break;
+            const size_t len = p->cp_bytes - i * COPY_PIECE < COPY_PIECE ? p->cp_bytes - i * COPY_PIECE : COPY_PIECE;
+            if (p->cp_src) memcpy(p->cp_dst + i * COPY_PIECE, p->cp_src + i * COPY_PIECE, len);
+            else memset(p->cp_dst + i * COPY_PIECE, 0, len);
+        }
+        return;
+    }
     for (;;) {
         const size_t b0 = atomic_fetch_add_explicit(&p->next, POOL_CHUNK, memory_order_relaxed);
         if (b0 >= p->nblocks) break;
@@ -290,6 +303,22 @@ void lz4cpu_pool_run(lz4cpu_pool *p, int decode, const uint8_t *in, const uint64
     p->in = in; p->in_off = in_off; p->in_len = in_len;
     p->out = out; p->out_off = out_off; p->out_cap = out_cap; p->out_len = out_len; p->status = status;
     p->nblocks = nblocks;
+    atomic_store(&p->next, 0);
+    p->running = p->nthreads;
+    p->generation++;
+    pthread_cond_broadcast(&p->cv_start);
+    while (p->running) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+}
+
+/* dst[0..n) = src[0..n) (src == NULL: zero fill), 1 MiB pieces handed to the pool's threads: a buffer the workers are going
+ * to stream through is first touched BY the workers, so its pages spread over the NUMA nodes instead of all sitting on the
+ * node of the thread that allocated it. */
+void lz4cpu_pool_copy(lz4cpu_pool *p, uint8_t *dst, const uint8_t *src, size_t n)
+{
+    pthread_mutex_lock(&p->mu);
+    p->decode = 2;
+    p->cp_dst = dst; p->cp_src = src; p->cp_bytes = n;
     atomic_store(&p->next, 0);
     p->running = p->nthreads;
     p->generation++;
