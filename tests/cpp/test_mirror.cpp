@@ -122,6 +122,24 @@ int main(int argc, char **argv)
         auto all = dec.read_to_end();
         CHECK(all.is_ok() && all.value() == d);
     }
+    {   // concatenated frames: read_to_end() stops at each EndMark (tests/tests.rs:633-647)
+        frame::FrameInfo info; info.block_size(frame::BlockSize::Max64KB);
+        const lz4b200_frame_info ci = info.to_c();
+        std::vector<uint8_t> a(d.begin(), d.begin() + 30000), b(d.begin() + 30000, d.end());
+        std::vector<uint8_t> fa(lz4b200_frame_bound(a.size(), &ci)), fb(lz4b200_frame_bound(b.size(), &ci));
+        size_t wa = 0, wb = 0;
+        CHECK(lz4b200_frame_compress(default_context(), a.data(), a.size(), &ci, a.size(), fa.data(), fa.size(), &wa) == LZ4B200_OK);
+        CHECK(lz4b200_frame_compress(default_context(), b.data(), b.size(), &ci, b.size(), fb.data(), fb.size(), &wb) == LZ4B200_OK);
+        std::vector<uint8_t> cat(fa.begin(), fa.begin() + (long)wa);
+        cat.insert(cat.end(), fb.begin(), fb.begin() + (long)wb);
+        frame::FrameDecoder dec(cat.data(), cat.size());
+        auto r1 = dec.read_to_end();
+        auto r2 = dec.read_to_end();
+        auto r3 = dec.read_to_end();
+        CHECK(r1.is_ok() && r1.value() == a);
+        CHECK(r2.is_ok() && r2.value() == b);
+        CHECK(r3.is_ok() && r3.value().empty());
+    }
     {
         frame::FrameInfo info; info.content_size(3);
         frame::FrameEncoder<VecSink> enc(VecSink{}, info);
