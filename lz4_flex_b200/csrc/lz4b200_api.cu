@@ -335,7 +335,7 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
 {
     const uint32_t per_cta = kDecWarpsPerCta * (32 / G);
     uint32_t want = (a.nblocks + per_cta - 1) / per_cta;
-    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * 16));
+    uint32_t grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * std::min(32, 64 / kDecWarpsPerCta)));   // 64 warps per SM
 #ifdef LZ4B200_AB_VARIANTS
     if (ctx->dec_ctas_override) grid = std::min<uint32_t>(want, (uint32_t)(ctx->sm_count * ctx->dec_ctas_override));
     if (!a.dict_len && ctx->dec_conv) { lz4_decompress_blocks_conv<G><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a); CTX_CUDA(ctx, cudaGetLastError()); return LZ4B200_OK; }

@@ -659,7 +659,10 @@ lz4_decompress_blocks_linked(BatchArgs a)
     }
 }
 
-constexpr int kDecWarpsPerCta = 4;
+#ifndef DEC_WARPS_PER_CTA
+#define DEC_WARPS_PER_CTA 4   // build-time A/B: smaller CTAs spread a batch that is resident all at once more evenly over the SMs
+#endif
+constexpr int kDecWarpsPerCta = DEC_WARPS_PER_CTA;
 
 // kDict: the batch has an external dictionary (decompress_into_with_dict); a separate instantiation so that the
 // plain kernel's register allocation is untouched (with the dictionary live ptxas spills in the hot loop: 4.2 -> 7.0 ms).
