@@ -131,3 +131,13 @@ def test_sharded_frame_gloo(world, total, bsid):
         assert p.exitcode == 0
     data = corpus.tiled("compression_66k_JSON.txt", total)
     assert got == oracle.frame_compress(data, bsid)
+
+
+def test_numa_helpers_degrade_gracefully():
+    """lz4_flex_b200/numa.py: cpulist parsing, and binding is a no-op (not an error) where the GPU's node is unknown."""
+    from lz4_flex_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert numa._parse_cpulist("") == []
+    info = numa.bind_to_gpu_node(0)
+    assert info["bound"] in (True, False)
+    numa.restore_affinity(info)
