@@ -488,7 +488,12 @@ def run_ours(args):
             best_chunks, e2e_s = nchunks, float(np.mean(ts))
         if rank == 0 and os.environ.get("LZ4B200_DEBUG"):
             print(f"# e2e pipelined x{nchunks}: {1e3 * float(np.mean(ts)):.2f} ms (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
+    per_rank = None
     if world > 1:
+        # every rank's own e2e time and NUMA placement go into the record (which ranks are the slow ones, and where they sit)
+        mine = {"rank": rank, "e2e_ms": 1e3 * e2e_s, **numa_rec}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
         t = torch.tensor([e2e_s, e2e_serial_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s, e2e_serial_s = float(t.cpu()[0]), float(t.cpu()[1])
@@ -560,7 +565,7 @@ def run_ours(args):
             "liblz4_anchor": liblz4_anchor(data, min(nb, 1024))},
         "e2e": {"value": world * mib_rank / e2e_s, "unit": "MiB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
-                "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks,
+                "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks, "per_rank": per_rank,
                 "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers); "
                        + ("one call each, back to back" if best_chunks == 1 else
                           f"batch cut into {best_chunks} chunks, compress of chunk c+1 and decompress of chunk c on two "
