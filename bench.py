@@ -469,25 +469,93 @@ def run_ours(args):
         if err:
             raise err[0]
 
-    best_chunks, e2e_s = 1, e2e_serial_s
-    for nchunks in ([2, 4, 8] if nb >= 4096 else []):
+    # A worker-pool caller (what a rayon-style user of the batch calls does): the batch is cut into chunks, `nc`
+    # threads (one context each) take chunks in order and compress them, `nd` threads decompress each chunk as soon
+    # as its compressed bytes are back on the host.  One call's tail (the last block's serial chain, ~5 ms, with the
+    # H2D link idle) overlaps the next call's copies, and compress H2D runs next to decompress D2H on the duplex link.
+    pool_ctx = {}
+    h_comp_slots = None
+
+    def pooled(nchunks, nc, nd):
+        nonlocal h_comp_slots
+        if h_comp_slots is None:
+            h_comp_slots = torch.empty(nb * slot, dtype=torch.uint8).pin_memory()   # worst-case region per chunk
+        per = -(-nb // nchunks)
+        todo = _queue.Queue()
+        done = _queue.Queue()
+        for b0 in range(0, nb, per):
+            todo.put((b0, min(nb, b0 + per)))
+        err = []
+        hs = h_comp_slots.numpy()
+
+        def cw(i):
+            c = pool_ctx.setdefault(("c", i), block.Context(local))
+            try:
+                while True:
+                    try:
+                        b0, b1 = todo.get_nowait()
+                    except _queue.Empty:
+                        break
+                    o, ooff, olen = block.compress_batch(h_in.numpy(), offs[b0:b1], lens[b0:b1], None,
+                                                         out=hs[b0 * slot:b1 * slot], ctx=c)
+                    done.put((b0, b1, ooff, olen))
+            except Exception as e:                      # noqa: BLE001
+                err.append(e)
+
+        def dw(i):
+            c = pool_ctx.setdefault(("d", i), block.Context(local, high_priority=True))
+            try:
+                while True:
+                    it = done.get()
+                    if it is None:
+                        break
+                    b0, b1, ooff, olen = it
+                    block.decompress_batch(hs[b0 * slot:b1 * slot], ooff, olen, h_back.numpy(), offs[b0:b1], lens[b0:b1], ctx=c)
+            except Exception as e:                      # noqa: BLE001
+                err.append(e)
+
+        cws = [threading.Thread(target=cw, args=(i,)) for i in range(nc)]
+        dws = [threading.Thread(target=dw, args=(i,)) for i in range(nd)]
+        for t in cws + dws:
+            t.start()
+        for t in cws:
+            t.join()
+        for _ in dws:
+            done.put(None)
+        for t in dws:
+            t.join()
+        if err:
+            raise err[0]
+
+    best_chunks, e2e_s, e2e_how = 1, e2e_serial_s, "one call each, back to back"
+    # measured on B200 (profiles/r2_e2e_callers.txt): serial 48.6 ms; pipelined x2/x4/x8 51.6 / 54.3 / 66.7; pooled (8,2,1) /
+    # (8,3,2) / (16,3,2) / (16,4,2) 63.9 / 59.9 / 64.7 / 63.8 — the encoder's persistent CTAs leave the decoder no warp slots,
+    # so overlapping the two calls only adds per-call tails.  Two probes stay so that the record shows the comparison was made.
+    cands = [("pipelined", (2,)), ("pooled", (8, 3, 2))]
+    if os.environ.get("LZ4B200_E2E_POOL"):               # tuning aid: "chunks,compress_threads,decompress_threads;..."
+        cands = [("pooled", tuple(int(v) for v in c.split(","))) for c in os.environ["LZ4B200_E2E_POOL"].split(";")]
+    for kind, cfg in (cands if nb >= 4096 else []):
         ts = []
-        for it in range(1 + e2e_steps):
+        for it in range(2 + e2e_steps):
             h_back.numpy()[::4096] = 0
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            pipelined(nchunks)
+            (pipelined if kind == "pipelined" else pooled)(*cfg)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            if it >= 1:
+            if it >= 2:
                 ts.append(dt)
         assert np.array_equal(h_back.numpy(), data)
         if float(np.mean(ts)) < e2e_s:
-            best_chunks, e2e_s = nchunks, float(np.mean(ts))
+            best_chunks, e2e_s = cfg[0], float(np.mean(ts))
+            e2e_how = (f"{cfg[0]} chunks, one compress thread feeding one decompress thread" if kind == "pipelined" else
+                       f"{cfg[0]} chunks, {cfg[1]} compress threads + {cfg[2]} decompress threads (one context each)")
         if rank == 0 and os.environ.get("LZ4B200_DEBUG"):
-            print(f"# e2e pipelined x{nchunks}: {1e3 * float(np.mean(ts)):.2f} ms (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
+            print(f"# e2e {kind} {cfg}: {1e3 * float(np.mean(ts)):.2f} ms (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
+    pool_ctx.clear()
+    h_comp_slots = None
     per_rank = None
     if world > 1:
         # every rank's own e2e time and NUMA placement go into the record (which ranks are the slow ones, and where they sit)
@@ -567,9 +635,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
                 "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks, "per_rank": per_rank,
                 "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers); "
-                       + ("one call each, back to back" if best_chunks == 1 else
-                          f"batch cut into {best_chunks} chunks, compress of chunk c+1 and decompress of chunk c on two "
-                          f"host threads / two contexts")},
+                       + e2e_how},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
         "numa": numa_rec,

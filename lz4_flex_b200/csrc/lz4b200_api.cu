@@ -264,6 +264,8 @@ struct lz4b200_ctx {
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_g16 = 0;                          // LZ4B200_ENC_G16=62|71 (16-lane groups) or 862|871 (8-lane groups): lane-group matchers, 0: off
     int enc_g16_ctas = 8;                     // LZ4B200_ENC_G16_CTAS
+    int enc_nib = 0;                          // LZ4B200_ENC_NIB=1: shared-memory nibble tags + first-2 verification (gnib)
+    int enc_nib_ctas = 8;                     // LZ4B200_ENC_NIB_CTAS
     // K1-S2 (one chain per CTA over the TMA-fed ring, lz4b200_solo_kernel.cuh): LZ4B200_ENC_SOLO=2 routes batches of
     // blocks > 64 KiB (and batches of at most enc_solo_small_max small blocks) to it
     int enc_solo = 0, enc_solo_ctas_per_sm = 0, enc_solo2_ctas_per_sm = 0;
@@ -341,9 +343,13 @@ lz4b200_status launch_decompress_g(lz4b200_ctx *ctx, const BatchArgs &a, cudaStr
     if (!a.dict_len && ctx->dec_conv) { lz4_decompress_blocks_conv<G><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a); CTX_CUDA(ctx, cudaGetLastError()); return LZ4B200_OK; }
     if (!a.dict_len && ctx->dec_batched) { lz4_decompress_blocks<G, 1, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a); CTX_CUDA(ctx, cudaGetLastError()); return LZ4B200_OK; }
 #endif
-    if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
+    const uint32_t warps = (a.nblocks + (32 / G) - 1) / (32 / G);
+    const bool one_warp = !a.dict_len && kDecWarpsPerCta > 1 && warps <= (uint32_t)ctx->sm_count * 32u;   // all resident as one-warp CTAs
+    if (one_warp) lz4_decompress_blocks<G, 0, false, 1><<<warps, 32, 0, s>>>(a);
+    else if (a.dict_len) lz4_decompress_blocks<G, 0, true><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
     else lz4_decompress_blocks<G, 0, false><<<grid, kDecWarpsPerCta * 32, 0, s>>>(a);
-    ctx->last_kernel[1] = G == 8 ? "lz4_decompress_blocks<8, 0, 0>" : G == 16 ? "lz4_decompress_blocks<16, 0, 0>" : "lz4_decompress_blocks<32, 0, 0>";
+    ctx->last_kernel[1] = one_warp ? (G == 8 ? "lz4_decompress_blocks<8, 0, 0, 1>" : G == 16 ? "lz4_decompress_blocks<16, 0, 0, 1>" : "lz4_decompress_blocks<32, 0, 0, 1>")
+                                   : (G == 8 ? "lz4_decompress_blocks<8, 0, 0, 4>" : G == 16 ? "lz4_decompress_blocks<16, 0, 0, 4>" : "lz4_decompress_blocks<32, 0, 0, 4>");
     CTX_CUDA(ctx, cudaGetLastError());
     return LZ4B200_OK;
 }
@@ -520,7 +526,11 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             const size_t region = (size_t)ctx->sm_count * chains_per_sm * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
-            if (ctx->enc_g16) {                                                      // 2 or 4 chains per matcher warp
+            if (ctx->enc_nib && !ctx->enc_g16) {                                     // nibble tags in shared memory
+                const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)(ctx->sm_count * ctx->enc_nib_ctas));
+                lz4_compress_blocks_gnib<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
+                ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1>";
+            } else if (ctx->enc_g16) {                                               // 2 or 4 chains per matcher warp
                 const int m = (ctx->enc_g16 % 100) / 10, gsz = ctx->enc_g16 >= 800 ? 8 : 16;   // 62 | 71 (G = 16), 862 | 871 (G = 8)
                 const int per_cta = (32 / gsz) * m;
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
@@ -665,6 +675,8 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     }
     if (const char *g = getenv("LZ4B200_ENC_G16")) ctx->enc_g16 = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_G16_CTAS")) ctx->enc_g16_ctas = std::max(1, std::min(8, atoi(g)));
+    if (const char *g = getenv("LZ4B200_ENC_NIB")) ctx->enc_nib = atoi(g);
+    if (const char *g = getenv("LZ4B200_ENC_NIB_CTAS")) ctx->enc_nib_ctas = std::max(1, std::min(8, atoi(g)));
     if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (ctx->enc_solo2_ctas_per_sm < 1 && ctx->enc_solo == 2) ctx->enc_solo = 0;

@@ -489,6 +489,200 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// Matcher with 4-bit tags in SHARED memory beside the global position table (lz4_compress_blocks_gnib).
+// What `gtab` pays for its 56 chains per SM is table and candidate traffic: every probe batch loads 32 table entries
+// and 32 candidates (3.8 G L2 sector requests, 41 GB of DRAM traffic per GiB — profiles/r2_l2_sectors_by_instruction.md)
+// although the sequential loop of compress.rs:373-439 stops at the first match, 2.4 probes in on JSON.  Here every
+// slot also has a 4-bit tag of the 4 bytes at its position, 2 KiB per chain in shared memory (8 x 7 chains = 112 KB per
+// SM).  A probe whose tag disagrees cannot pass the 4-byte comparison (compress.rs:432-438), so it touches neither the
+// table nor its candidate.  The tag-matching probes are verified TWO at a time in probe order and the search stops at
+// the first real hit — exactly the probes the sequential loop would have executed, plus at most one.  Exactness of the
+// in-batch forwarding is kept as in match_block: clashes among the probes up to the hit are detected (three shuffles /
+// match.any) and re-evaluated register to register; if that takes the hit away and nothing before it matches, the probes
+// up to there are committed and the batch continues behind them inside the same 32-probe step group (`gi`).
+// Model + proof against the oracle: tests/test_warp_emulation.py::warp_encode_nib.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tag4(uint32_t v4) { return (v4 * 2246822519u) >> 28; }
+
+__device__ __forceinline__ void nib_put(uint32_t *nt, uint32_t slot, uint32_t tag)
+{
+    const uint32_t sh = (slot & 7u) * 4u;
+    atomicAnd(nt + (slot >> 3), ~(15u << sh));                  // lanes of one commit own different nibbles
+    atomicOr(nt + (slot >> 3), tag << sh);
+}
+
+template <typename View>
+__device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t *tab, uint32_t *nt,
+                                                bool cont, bool h5, SeqProducer &pr, uint32_t lane)
+{
+    constexpr uint32_t kInvalid = TabTraits<uint16_t>::kInvalid;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    if (n < 13) {                                               // compress.rs:343-346
+        pr.push_final(0, n, lane);
+        return;
+    }
+    view.advance(0u);
+    {
+        const uint32_t f = cont ? 0xffffffffu : 0u;
+        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
+#pragma unroll 4
+        for (uint32_t i = lane; i < 4096u * 2u / 16u; i += 32) tab_fill16<true>(t128 + i, f);
+        uint32_t lo0, hi0; view.ro5(0, lo0, hi0);               // an empty slot is a candidate at position 0: its tag
+        const uint32_t t = tag4(lo0) * 0x11111111u;
+        uint4 *n128 = reinterpret_cast<uint4 *>(nt);
+#pragma unroll
+        for (uint32_t i = lane; i < 2048u / 16u; i += 32) n128[i] = make_uint4(t, t, t, t);
+        __syncwarp();
+    }
+    const uint32_t last_probe = n - 12;
+    const uint32_t lim = n - 6;
+    uint32_t anchor = 0, cur = 0;
+    bool ri = false;
+    if (!cont) {                                                // compress.rs:353-359
+        uint32_t lo, hi; view.ro5(0, lo, hi);
+        const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
+        if (lane == 0) { tab_put<true>(tab, s, 0u); nib_put(nt, s, tag4(lo)); }
+        cur = 1;
+        __syncwarp();
+    }
+
+    for (;;) {                                                  // one sequence per iteration
+        uint32_t gbase = cur, stride = 1, gi = 0, cand, mpos;
+        for (;;) {                                              // probe batches: compress.rs:373-439
+            const uint32_t width = 32u - gi;
+            const uint32_t base = gbase + gi * stride;
+            view.advance(base);
+            const uint32_t p = base + lane * stride;
+            const bool act = lane < width;
+            const bool term = act && p > last_probe;
+            const bool live = act && !term;
+            uint32_t v4, hi;
+            view.ro5(live ? p : 0u, v4, hi);
+            if (ri) {                                           // compress.rs:460-461, before this batch's table reads
+                uint32_t lo2, hi2;
+                view.ro5(cur - 2u, lo2, hi2);
+                const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+                if (lane == 0) { tab_put<true>(tab, s2, cur - 2u); nib_put(nt, s2, tag4(lo2)); }
+                __syncwarp();
+                ri = false;
+            }
+            uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
+            const uint32_t mytag = tag4(v4);
+            bool tm = false;
+            if (live) tm = ((nt[key >> 3] >> ((key & 7u) * 4u)) & 15u) == mytag; else key = 0x10000u | lane;
+            uint32_t pend = __ballot_sync(kFull, tm);
+            uint32_t cnd = kInvalid, hits = 0;
+            bool hit = false;
+            while (pend) {                                      // verify the tag-matching probes two at a time, in order
+                const uint32_t rest = pend & (pend - 1u), rest2 = rest & (rest - 1u);
+                const bool sel = ((pend & ~rest2) >> lane) & 1u;
+                if (sel) {
+                    cnd = tab_get<true>(tab, key);
+                    const bool chk = cnd != kInvalid && p - cnd <= 65535u;
+                    hit = chk && view.ro4(chk ? cnd : 0u) == v4;
+                }
+                hits = __ballot_sync(kFull, sel && hit);
+                if (hits) break;
+                pend = rest2;
+            }
+            const uint32_t terms = (gbase + 31u * stride > last_probe) ? __ballot_sync(kFull, term) : 0u;
+            const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : 32u;
+            const uint32_t upto0 = w0 < width ? w0 : width - 1u;
+            uint32_t same = 1u << lane, win = w0;
+            bool exact = w0 == 0u;
+            if (w0 >= 1u && w0 <= 3u) {
+                const uint32_t k0 = __shfl_sync(kFull, key, 0), k1 = __shfl_sync(kFull, key, 1), k2 = __shfl_sync(kFull, key, 2);
+                const bool clash = (lane >= 1u && key == k0) || (lane >= 2u && key == k1) || (lane >= 3u && key == k2);
+                exact = (__ballot_sync(kFull, clash && lane <= w0) == 0u);
+            }
+            if (!exact) {
+                same = __match_any_sync(kFull, key);
+                const uint32_t prior = same & lt_mask;
+                const uint32_t le0 = upto0 >= 31u ? kFull : ((2u << upto0) - 1u);
+                if (__ballot_sync(kFull, prior != 0u) & le0) {
+                    const uint32_t pl = prior ? 31u - __clz(prior) : lane;   // the forwarded candidate is a probe of this
+                    const uint32_t pv = __shfl_sync(kFull, v4, pl);          // batch: its 4 bytes sit in that lane's register
+                    if (prior) { cnd = base + pl * stride; hit = pv == v4; }
+                    const uint32_t h2 = __ballot_sync(kFull, hit) & le0;
+                    win = h2 ? (uint32_t)__ffs(h2) - 1u : 32u;
+                }
+            }
+            const bool partial = win == 32u && w0 < 32u;        // forwarding took the hit away: probes 0..w0 were executed
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : 32u;
+            if (!partial && tfirst < win) {                     // compress.rs:381-384: the rest is literals
+                pr.push_final(anchor, n, lane);
+                return;
+            }
+            const uint32_t upto = partial ? w0 : (win < 32u ? win : width - 1u);
+            const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
+            const uint32_t mine = same & le_mask;
+            if (lane <= upto && (31u - __clz(mine)) == lane) { tab_put<true>(tab, key, p); nib_put(nt, key, mytag); }
+            __syncwarp();
+            if (win < 32u) {
+                mpos = base + win * stride;
+                cand = __shfl_sync(kFull, cnd, win);
+                break;
+            }
+            gi += upto + 1u;
+            if (gi == 32u) { gbase += 32u * stride; stride++; gi = 0; }
+        }
+        const uint32_t dist = mpos - cand;
+
+        // ---- extension (as match_block_view): first forward round and the backward round share one round trip
+        const uint32_t room = min(cand, mpos - anchor);
+        const uint32_t qf = mpos + 4u + lane;
+        const bool inf = qf < lim;
+        const uint8_t f1 = view.byte(inf ? qf : mpos);
+        const uint8_t f2 = view.byte((inf ? qf : mpos) - dist);
+        uint32_t kb = 0;
+        if (room) {                                             // compress.rs:272-287
+            const bool inb = lane < room;
+            const uint8_t b1 = view.byte(mpos - (inb ? 1u + lane : 0u)), b2 = view.byte(cand - (inb ? 1u + lane : 0u));
+            const uint32_t bad = ~__ballot_sync(kFull, inb && b1 == b2);
+            kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+        }
+        const uint32_t badf = ~__ballot_sync(kFull, inf && f1 == f2);
+        const uint32_t kf = badf ? (uint32_t)__ffs(badf) - 1u : 32u;
+        uint32_t end = mpos + 4u + kf;
+        if (kb) {
+            mpos -= kb; cand -= kb;
+            while (kb == 32u) {
+                const uint32_t room2 = min(cand, mpos - anchor);
+                const bool inb = lane < room2;
+                const uint8_t b1 = view.byte(mpos - (inb ? 1u + lane : 0u)), b2 = view.byte(cand - (inb ? 1u + lane : 0u));
+                const uint32_t bad = ~__ballot_sync(kFull, inb && b1 == b2);
+                kb = bad ? (uint32_t)__ffs(bad) - 1u : 32u;
+                mpos -= kb; cand -= kb;
+            }
+        }
+        if (kf == 32u) {                                        // long match: 128 bytes per round (compress.rs:156-216)
+            for (;;) {
+                view.advance(end);
+                const uint32_t pos = end + 4u * lane;
+                const bool full = pos + 4u <= lim;
+                const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
+                const uint32_t nm = full ? (x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u) : 0u;
+                const uint32_t bad = __ballot_sync(kFull, nm < 4u);
+                if (bad) {
+                    const uint32_t fl = (uint32_t)__ffs(bad) - 1u;
+                    end += 4u * fl + __shfl_sync(kFull, nm, fl);
+                    break;
+                }
+                end += 128u;
+            }
+            if (end < lim) {
+                const uint32_t q = end + lane;
+                const bool ok = lane < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
+                end += (uint32_t)__ffs(~__ballot_sync(kFull, ok)) - 1u;
+            }
+        }
+        pr.push(anchor, mpos, dist, end, lane);
+        anchor = cur = end;
+        ri = true;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // matcher with an external dictionary: compress_into_with_dict (compress.rs:554-583, 610-616).
 // The dictionary logically precedes the input: the table holds STREAM positions (input position + dictionary
 // length), init_dict seeds it with every third dictionary position, and a candidate below the dictionary
@@ -844,6 +1038,49 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
     else
         matcher_loop<TabT, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
+    retire_warp(tickets, gridDim.x * kM);
+}
+
+// Global position tables + shared-memory nibble tags (match_block_nib): kM matchers + kE emitters per CTA.
+// Blocks of at most 65 536 bytes, no dictionary.
+template <int kM, int kE>
+__global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
+lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
+{
+    constexpr int kR = kM / kE;
+    static_assert(kM % kE == 0, "every emitter serves the same number of matchers");
+    __shared__ __align__(16) uint32_t nt_s[kM * 512];        // 4096 nibbles per matcher
+    __shared__ __align__(16) uint4 q_s[kM * 2 * kSeqBatchEntries];
+    __shared__ uint32_t meta_s[kM * 8];
+    __shared__ __align__(8) uint64_t bars_s[kM * 4];
+    __shared__ EmitState st_s[kM];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x < (uint32_t)kM * 4u) mbar_init(bars_s + threadIdx.x, 1u);
+    __syncthreads();
+    if (warp >= (uint32_t)kM) {
+        const uint32_t e = warp - kM;
+        emit_loop_multi<kR>(a, q_s + e * kR * 2 * kSeqBatchEntries, meta_s + e * kR * 8, bars_s + e * kR * 4,
+                            st_s + e * kR, lane);
+        return;
+    }
+    SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    uint16_t *tab = gtab + ((size_t)blockIdx.x * kM + warp) * 4096;
+    uint32_t *nt = nt_s + warp * 512;
+    for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
+        const uint32_t n = a.in_len[b];
+        if (n > 65536u) continue;                                           // the u32 kernel's block
+        const uint32_t fl = a.flags ? a.flags[b] : 0u;
+        if ((uint64_t)a.out_cap[b] < max_output_size_dev(n)) {              // compress.rs:338-340
+            if (lane == 0) { a.out_len[b] = 0; a.status[b] = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; }
+            continue;
+        }
+        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
+        pr.block = b; pr.first = 1;
+        WordView view(a.in + a.in_off[b]);
+        match_block_nib(view, n, tab, nt, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
+    }
+    pr.block = kExitBlock; pr.first = 0;
+    pr.flush(0, lane);
     retire_warp(tickets, gridDim.x * kM);
 }
 

@@ -72,6 +72,10 @@ elif MODE == "thread":
     run({"LZ4B200_THREAD_MIN": "4000000000"}, "round-1 warp kernels (gtab / G=8)")
     for lanes in (32, 16, 8):
         run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
+elif MODE == "nib":
+    run({}, "gtab 7+1 x8 (default)")
+    for ctas in (8, 7, 6, 5):
+        run({"LZ4B200_ENC_NIB": "1", "LZ4B200_ENC_NIB_CTAS": str(ctas)}, f"smem nibble tags + first-2 verify, {ctas} CTAs/SM", iters=4)
 elif MODE == "g16":
     run({}, "gtab 7+1 x8 (round 1 default)")
     for shape, ctas_list in (("71", (8, 4)), ("871", (8, 4, 2)), ("862", (8,))):

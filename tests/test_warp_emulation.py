@@ -199,3 +199,163 @@ def test_lane_group_batches_keep_the_parse(name, data):
         assert warp_encode(data, G=G) == oracle.compress_block(data)
         assert warp_encode(data, cont=True, h5=True, G=G) == oracle.compress_block_cont(data)
         assert warp_encode(data, cont=False, h5=True, G=G) == oracle.compress_block_fresh_h5(data)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# lz4_compress_blocks_gnib: 4-bit tags in SHARED memory beside the global position table, candidates verified first-K.
+# ---------------------------------------------------------------------------------------------------------------------
+def _tag4(b, p):
+    return ((int.from_bytes(b[p:p + 4], "little") * 2246822519) & 0xFFFFFFFF) >> 28
+
+
+def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 2) -> bytes:
+    """Model of match_block_view<kNib>: every slot has a 4-bit tag of the 4 bytes at its position (shared memory); a probe
+    whose tag disagrees cannot pass the 4-byte comparison (compress.rs:432-438), so it touches neither the position table
+    nor the candidate.  The tag-matching probes of a batch are verified K at a time in probe order and the search stops at
+    the first real hit — the sequential loop never looks past it either.  If in-batch forwarding (an earlier probe of the
+    batch owns the slot) takes the hit away and nothing at or before it matches, the probes up to there are committed and
+    the batch continues behind them inside the same 32-probe step group (`gi`)."""
+    n = len(b)
+    if n < 13:
+        return _last_literals(b, 0)
+    if h5 is None:
+        h5 = n >= 65535
+    H = _h5 if h5 else _h4
+    tab = [INVALID if cont else 0] * 4096
+    ntag = [_tag4(b, 0) if n >= 4 else 0] * 4096                 # FRESH: empty slot = position 0 (cont: value irrelevant)
+    last_probe, lim = n - 12, n - 6
+    out = bytearray()
+    anchor = cur = 0
+    ri = False
+    st = stats if stats is not None else {}
+    for k in ("seqs", "batches", "rounds", "tab_loads", "cand_loads", "partial", "slow"):
+        st.setdefault(k, 0)
+    if not cont:
+        tab[H(b, 0)] = 0
+        ntag[H(b, 0)] = _tag4(b, 0)
+        cur = 1
+    R = range(32)
+    while True:
+        gbase, stride, gi = cur, 1, 0
+        while True:
+            width = 32 - gi
+            p = [gbase + (gi + i) * stride for i in R]
+            act = [i < width for i in R]
+            term = [act[i] and p[i] > last_probe for i in R]
+            live = [act[i] and not term[i] for i in R]
+            if ri:
+                tab[H(b, cur - 2)] = cur - 2
+                ntag[H(b, cur - 2)] = _tag4(b, cur - 2)
+                ri = False
+            key = [H(b, p[i]) if live[i] else (0x10000 | i) for i in R]
+            mytag = [_tag4(b, p[i]) if live[i] else 16 for i in R]
+            pend = [i for i in R if live[i] and ntag[key[i]] == mytag[i]]
+            st["batches"] += 1
+            hit = [False] * 32
+            cnd = [INVALID] * 32
+
+            def verify(i):
+                c = tab[key[i]]
+                st["tab_loads"] += 1
+                cnd[i] = c
+                if c == INVALID or p[i] - c > 65535:
+                    return False
+                st["cand_loads"] += 1
+                return b[c:c + 4] == b[p[i]:p[i] + 4]
+
+            while pend:
+                sel, pend = pend[:K], pend[K:]
+                st["rounds"] += 1
+                for i in sel:
+                    hit[i] = verify(i)
+                if any(hit[i] for i in sel):
+                    break
+            w0 = hit.index(True) if True in hit else 32
+            upto0 = min(w0, width - 1)
+            exact = w0 == 0
+            if 1 <= w0 <= 3:
+                exact = not any(key[j] == key[i] for j in range(1, w0 + 1) for i in range(j))
+            same = [[i] for i in R]
+            win = w0
+            if not exact:
+                same = [[j for j in R if key[j] == key[i]] for i in R]
+                prior = [[j for j in same[i] if j < i] for i in R]
+                if any(prior[i] for i in range(upto0 + 1)):
+                    st["slow"] += 1
+                    for i in range(upto0 + 1):
+                        if prior[i]:                             # forwarded candidate: lane-to-lane compare, no memory
+                            cnd[i] = p[prior[i][-1]]
+                            hit[i] = b[cnd[i]:cnd[i] + 4] == b[p[i]:p[i] + 4]
+                    hh = [hit[i] for i in range(upto0 + 1)]
+                    win = hh.index(True) if True in hh else 32
+            tfirst = term.index(True) if True in term else 32
+            if win == 32 and w0 < 32 and tfirst > w0:
+                # forwarding took the hit at w0 away and nothing before it matches: lanes 0..w0 were executed probes
+                upto = w0
+                st["partial"] += 1
+            else:
+                if tfirst < win:                                 # compress.rs:381-384
+                    return bytes(out) + _last_literals(b, anchor)
+                upto = win if win < 32 else width - 1
+            for i in range(upto + 1):
+                if max(j for j in same[i] if j <= upto) == i:
+                    tab[key[i]] = p[i]
+                    ntag[key[i]] = mytag[i]
+            if win < 32:
+                mpos, cand = p[win], cnd[win]
+                break
+            gi += upto + 1
+            if gi == 32:
+                gbase += 32 * stride
+                stride += 1
+                gi = 0
+        dist = mpos - cand
+        while cand > 0 and mpos > anchor and b[mpos - 1] == b[cand - 1]:
+            mpos -= 1; cand -= 1
+        end, c = mpos + 4, cand + 4
+        while end < lim and b[end] == b[c]:
+            end += 1; c += 1
+        lit, extra = mpos - anchor, end - mpos - 4
+        out.append((min(lit, 15) << 4) | min(extra, 15))
+        if lit >= 15:
+            out += _ext(lit - 15)
+        out += b[anchor:mpos]
+        out += dist.to_bytes(2, "little")
+        if extra >= 15:
+            out += _ext(extra - 15)
+        anchor = cur = end
+        ri = True
+        st["seqs"] += 1
+
+
+@pytest.mark.parametrize("name,data", CASES, ids=[c[0] for c in CASES])
+def test_nibble_tags_first_k_keep_the_parse(name, data):
+    for K in (1, 2, 4):
+        assert warp_encode_nib(data, K=K) == oracle.compress_block(data)
+        assert warp_encode_nib(data, cont=True, h5=True, K=K) == oracle.compress_block_cont(data)
+        assert warp_encode_nib(data, cont=False, h5=True, K=K) == oracle.compress_block_fresh_h5(data)
+
+
+def test_nibble_tags_cut_the_table_and_candidate_traffic():
+    """On a JSON block the untagged matcher loads 32 table entries and 32 candidates per batch; first-2 verification behind
+    4-bit tags needs ~1 table load and ~1 candidate load per batch."""
+    data = corpus.tiled("compression_66k_JSON.txt", 65536).tobytes()
+    s = {}
+    assert warp_encode_nib(data, h5=True, stats=s) == oracle.compress_block_fresh_h5(data)
+    assert s["tab_loads"] < 3 * s["batches"] and s["cand_loads"] < 3 * s["batches"], s
+
+
+def test_nibble_partial_batches_happen():
+    """The continued batch (forwarding removes the speculative hit, nothing before it matches) is a real path: low-entropy
+    noise and word soup reach it a few times per block, still byte-identical to the oracle."""
+    rng = np.random.default_rng(5)
+    partial = 0
+    for a in (2, 13, 15, 21):
+        data = rng.integers(0, a, 20000, dtype=np.uint8).tobytes()
+        words = [rng.integers(0, 256, int(rng.integers(3, 9)), dtype=np.uint8).tobytes() for _ in range(a * 8)]
+        soup = b"".join(words[int(i)] for i in rng.integers(0, len(words), 4000))
+        for x in (data, soup):
+            s = {}
+            assert warp_encode_nib(x, stats=s) == oracle.compress_block(x)
+            partial += s["partial"]
+    assert partial >= 5, partial

@@ -4,7 +4,8 @@ environment switches (a fresh context reads them at creation):
   K1-T / K2-T  one block per thread          (lz4b200_thread_kernels.cuh)   LZ4B200_THREAD_MIN=1
   K1-S / K1-S2 one chain per CTA, smem ring  (lz4b200_solo_kernel.cuh)      LZ4B200_ENC_SOLO=1|2, _SOLO_SMALL_MAX=1000000
   warp kernels matcher/emitter warps, lane groups (default)                 LZ4B200_THREAD_MIN=4e9, LZ4B200_ENC_SOLO=0
-               (LZ4B200_ENC_GTAG=71: tagged table entries; LZ4B200_ENC_G16=62: two chains per matcher warp)
+               (LZ4B200_ENC_GTAG=71: tagged table entries; LZ4B200_ENC_G16=62: two chains per matcher warp;
+                LZ4B200_ENC_NIB=1: shared-memory nibble tags, first-2 verification)
 Bit-exact compressed bytes in all three parse modes, exact round trips, identical error codes / expected fields."""
 import os
 
@@ -29,6 +30,8 @@ VARIANTS = {
     "warp_half71": {"LZ4B200_ENC_G16": "71"},
     "warp_quarter": {"LZ4B200_ENC_G16": "871"},
     "warp_quarter62": {"LZ4B200_ENC_G16": "862", "LZ4B200_ENC_G16_CTAS": "6"},
+    "warp_nib": {"LZ4B200_ENC_NIB": "1"},
+    "warp_nib6": {"LZ4B200_ENC_NIB": "1", "LZ4B200_ENC_NIB_CTAS": "6"},
 }
 
 
@@ -164,6 +167,16 @@ def test_many_blocks_global_table_kernels(vctx):
     d = np.frombuffer(corpus.load("dickens.txt"), dtype=np.uint8)
     src[20 << 20: (20 << 20) + d.size] = d
     rng = np.random.default_rng(77)
+    # low-entropy noise and word soup: slot clashes inside a probe batch with real matches behind them — the in-batch
+    # forwarding paths (and gnib's continued batch, tests/test_warp_emulation.py::test_nibble_partial_batches_happen)
+    at = 31 << 20
+    for a in (2, 3, 5, 8, 13, 21, 34):
+        src[at: at + (1 << 19)] = rng.integers(0, a, 1 << 19, dtype=np.uint8)
+        at += 1 << 19
+        words = [rng.integers(0, 256, int(rng.integers(3, 9)), dtype=np.uint8) for _ in range(a * 8)]
+        soup = np.concatenate([words[int(i)] for i in rng.integers(0, len(words), 120000)])[: 1 << 19]
+        src[at: at + soup.size] = soup
+        at += 1 << 19
     lens = rng.integers(1500, 12000, 6000).astype(np.uint32)
     lens[:64] = np.arange(64, dtype=np.uint32)
     lens[64:80] = 65536
