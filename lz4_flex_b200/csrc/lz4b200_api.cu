@@ -526,10 +526,12 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
             const size_t region = (size_t)ctx->sm_count * chains_per_sm * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
-            if (ctx->enc_nib && !ctx->enc_g16) {                                     // nibble tags in shared memory
-                const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)(ctx->sm_count * ctx->enc_nib_ctas));
-                lz4_compress_blocks_gnib<7, 1><<<grid, 256, 0, s>>>(a, tickets + 2, gt);
-                ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1>";
+            if (ctx->enc_nib && !ctx->enc_g16) {                                     // tags in shared memory: 1 = nibbles x 8 CTAs, 2 = bytes x 6 CTAs, 3 = nibbles x 6 CTAs (40 registers)
+                const uint32_t ctas = std::min(ctx->enc_nib_ctas, ctx->enc_nib == 1 ? 8 : 6);
+                const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * ctas);
+                if (ctx->enc_nib == 2) { lz4_compress_blocks_gnib<7, 1, 8, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 8, 6>"; }
+                else if (ctx->enc_nib == 3) { lz4_compress_blocks_gnib<7, 1, 4, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 6>"; }
+                else { lz4_compress_blocks_gnib<7, 1, 4, 8><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 8>"; }
             } else if (ctx->enc_g16) {                                               // 2 or 4 chains per matcher warp
                 const int m = (ctx->enc_g16 % 100) / 10, gsz = ctx->enc_g16 >= 800 ? 8 : 16;   // 62 | 71 (G = 16), 862 | 871 (G = 8)
                 const int per_cta = (32 / gsz) * m;
@@ -979,11 +981,17 @@ static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *
     std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
     std::vector<uint32_t> h_cap(nb);
     uint32_t max_len = 0;
+    uint64_t remaining = 0;
+    for (uint32_t b = 0; b < nb; b++) remaining += in_len[b];
     for (uint32_t b = 0; b < nb;) {
         Chunk c{b, b, ~0ull, 0, 0, 0};
         uint64_t bytes = 0;
-        // ramp: the first chunks are small (32, 64, ... MiB) so the first kernel starts after a short copy
-        const uint64_t limit = std::min<uint64_t>(kCompressChunkBytes, (32ull << 20) << std::min<size_t>(chunks.size(), 8));
+        // ramp up: the first chunks are small (32, 64, ... MiB) so the first kernel starts after a short copy;
+        // ramp down: the call ends one block's chain (~4.4 ms) after the LAST chunk's copy, plus that chunk's size read-back,
+        // pack and D2H — so the last chunks shrink again (..., 64, 32 MiB) and the earlier ones finish inside that tail
+        const uint64_t up = (32ull << 20) << std::min<size_t>(chunks.size(), 8);
+        const uint64_t down = std::max<uint64_t>(32ull << 20, remaining / 2);
+        const uint64_t limit = std::min<uint64_t>(kCompressChunkBytes, std::min(up, down));
         while (c.b1 < nb && (c.b1 == c.b0 || bytes + in_len[c.b1] <= limit)) {
             const uint32_t k = c.b1++;
             c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]);
@@ -999,6 +1007,7 @@ static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *
         for (uint32_t k = c.b0; k < c.b1; k++) h_in_off[k] = in_off[k] - c.in_lo;
         chunks.push_back(c);
         b = c.b1;
+        remaining -= std::min(remaining, bytes);
     }
     const uint32_t nch = (uint32_t)chunks.size();
     CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));

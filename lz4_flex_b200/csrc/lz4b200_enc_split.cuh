@@ -211,10 +211,26 @@ struct InputWindow {
 // Global tables are accessed with an L2 evict_last policy (createpolicy is a constant: it folds into the access
 // descriptor): 66 MB of tables must stay resident in the 126 MB L2 while ~0.5 GB of input streams through it —
 // without the hint the tables are evicted and every probe becomes a DRAM read (27.6 GB read per GiB compressed).
+// Both measured on B200 (profiles/r2_sweep_gnib_v2.txt): the global-table kernels are bound by instruction issue (~0.8 G
+// warp-instructions per ms whatever the variant), and with 32 registers per thread the compiler re-derives a chain's table
+// pointer from blockIdx / threadIdx and rebuilds the createpolicy descriptor (5 uniform instructions) at every table access.
+//   ENC_TAB_OPAQUE = 1: the chain's table offset lives in one opaque 32-bit register            17.77 -> 17.45 ms
+//   ENC_POLICY_HOIST = 1: createpolicy may be hoisted (uniform registers)                 with opaque: 17.17 ms
+//   ENC_POLICY_HOIST = 2: u16 table accesses without the evict_last hint (the hint was neutral)  with opaque: 16.46 ms (dickens 37.35 -> 34.55)
+#ifndef ENC_POLICY_HOIST
+#define ENC_POLICY_HOIST 2
+#endif
+#ifndef ENC_TAB_OPAQUE
+#define ENC_TAB_OPAQUE 1
+#endif
 __device__ __forceinline__ uint64_t l2_keep_policy()
 {
     uint64_t pol;
+#if ENC_POLICY_HOIST
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#else
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
     return pol;
 }
 template <bool kGT>
@@ -224,6 +240,8 @@ __device__ __forceinline__ uint32_t tab_get(const uint16_t *tab, uint32_t slot)
         uint16_t v;
 #if ENC_GTAB_L1
         asm volatile("ld.global.ca.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
+#elif ENC_POLICY_HOIST == 2
+        asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(tab + slot) : "memory");
 #else
         asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(tab + slot), "l"(l2_keep_policy()) : "memory");
 #endif
@@ -242,9 +260,13 @@ __device__ __forceinline__ uint32_t tab_get(const uint32_t *tab, uint32_t slot)
 template <bool kGT>
 __device__ __forceinline__ void tab_put(uint16_t *tab, uint32_t slot, uint32_t v)
 {
-    if constexpr (kGT)
+    if constexpr (kGT) {
+#if ENC_POLICY_HOIST == 2
+        asm volatile("st.global.cg.u16 [%0], %1;" ::"l"(tab + slot), "h"((uint16_t)v) : "memory");
+#else
         asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(tab + slot), "h"((uint16_t)v), "l"(l2_keep_policy()) : "memory");
-    else tab[slot] = (uint16_t)v;
+#endif
+    } else tab[slot] = (uint16_t)v;
 }
 template <bool kGT>
 __device__ __forceinline__ void tab_put(uint32_t *tab, uint32_t slot, uint32_t v)
@@ -502,17 +524,51 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
 // up to there are committed and the batch continues behind them inside the same 32-probe step group (`gi`).
 // Model + proof against the oracle: tests/test_warp_emulation.py::warp_encode_nib.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tag4(uint32_t v4) { return (v4 * 2246822519u) >> 28; }
+// Tag storage: kTagBits = 4 -> nibbles, 2 KiB per chain, updated with two shared-memory reductions (lanes of one commit
+// may own different nibbles of a word); kTagBits = 8 -> bytes, 4 KiB per chain, plain byte stores.  The chain's tag array
+// and its table are addressed through two opaque 32-bit values (a shared-memory address and a byte offset from the table
+// base): with 32-40 registers per thread the compiler otherwise re-derives both pointers from threadIdx / blockIdx in
+// every divergent block (~30 instructions each, profiles/r2_ncu_gnib.md).
+template <int kTagBits> __device__ __forceinline__ uint32_t tagof(uint32_t v4) { return (v4 * 2246822519u) >> (32 - kTagBits); }
 
-__device__ __forceinline__ void nib_put(uint32_t *nt, uint32_t slot, uint32_t tag)
+__device__ __forceinline__ uint32_t opaque32(uint32_t v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
+
+template <int kTagBits>
+__device__ __forceinline__ uint32_t tag_get(uint32_t nt_sa, uint32_t slot)
 {
-    const uint32_t sh = (slot & 7u) * 4u;
-    atomicAnd(nt + (slot >> 3), ~(15u << sh));                  // lanes of one commit own different nibbles
-    atomicOr(nt + (slot >> 3), tag << sh);
+    uint32_t v;
+    if constexpr (kTagBits == 8) {
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(nt_sa + slot) : "memory");
+        return v;
+    } else {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nt_sa + ((slot >> 1) & ~3u)) : "memory");
+        return (v >> ((slot & 7u) * 4u)) & 15u;
+    }
+}
+template <int kTagBits>
+__device__ __forceinline__ void tag_put(uint32_t nt_sa, uint32_t slot, uint32_t tag)
+{
+    if constexpr (kTagBits == 8) {
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(nt_sa + slot), "r"(tag) : "memory");
+    } else {
+        const uint32_t sa = nt_sa + ((slot >> 1) & ~3u), sh = (slot & 7u) * 4u;
+        asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(sa), "r"(~(15u << sh)) : "memory");
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(tag << sh) : "memory");
+    }
+}
+__device__ __forceinline__ uint32_t gpos_get(const uint8_t *gtab, uint32_t tab_off, uint32_t slot)
+{
+    uint16_t v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(gtab + (tab_off + slot * 2u)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void gpos_put(uint8_t *gtab, uint32_t tab_off, uint32_t slot, uint32_t pos)
+{
+    asm volatile("st.global.cg.u16 [%0], %1;" ::"l"(gtab + (tab_off + slot * 2u)), "h"((uint16_t)pos) : "memory");
 }
 
-template <typename View>
-__device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t *tab, uint32_t *nt,
+template <int kTagBits, typename View>
+__device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint8_t *gtab, uint32_t tab_off, uint32_t nt_sa,
                                                 bool cont, bool h5, SeqProducer &pr, uint32_t lane)
 {
     constexpr uint32_t kInvalid = TabTraits<uint16_t>::kInvalid;
@@ -524,14 +580,15 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t
     view.advance(0u);
     {
         const uint32_t f = cont ? 0xffffffffu : 0u;
-        uint4 *t128 = reinterpret_cast<uint4 *>(tab);
+        uint4 *t128 = reinterpret_cast<uint4 *>(gtab + tab_off);
 #pragma unroll 4
-        for (uint32_t i = lane; i < 4096u * 2u / 16u; i += 32) tab_fill16<true>(t128 + i, f);
+        for (uint32_t i = lane; i < 4096u * 2u / 16u; i += 32)
+            asm volatile("st.global.cg.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(t128 + i), "r"(f) : "memory");
         uint32_t lo0, hi0; view.ro5(0, lo0, hi0);               // an empty slot is a candidate at position 0: its tag
-        const uint32_t t = tag4(lo0) * 0x11111111u;
-        uint4 *n128 = reinterpret_cast<uint4 *>(nt);
+        const uint32_t t = tagof<kTagBits>(lo0) * (kTagBits == 8 ? 0x01010101u : 0x11111111u);
 #pragma unroll
-        for (uint32_t i = lane; i < 2048u / 16u; i += 32) n128[i] = make_uint4(t, t, t, t);
+        for (uint32_t i = lane; i < 4096u * kTagBits / 8u / 16u; i += 32)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(nt_sa + i * 16u), "r"(t) : "memory");
         __syncwarp();
     }
     const uint32_t last_probe = n - 12;
@@ -541,7 +598,7 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t
     if (!cont) {                                                // compress.rs:353-359
         uint32_t lo, hi; view.ro5(0, lo, hi);
         const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
-        if (lane == 0) { tab_put<true>(tab, s, 0u); nib_put(nt, s, tag4(lo)); }
+        if (lane == 0) { gpos_put(gtab, tab_off, s, 0u); tag_put<kTagBits>(nt_sa, s, tagof<kTagBits>(lo)); }
         cur = 1;
         __syncwarp();
     }
@@ -562,14 +619,14 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t
                 uint32_t lo2, hi2;
                 view.ro5(cur - 2u, lo2, hi2);
                 const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
-                if (lane == 0) { tab_put<true>(tab, s2, cur - 2u); nib_put(nt, s2, tag4(lo2)); }
+                if (lane == 0) { gpos_put(gtab, tab_off, s2, cur - 2u); tag_put<kTagBits>(nt_sa, s2, tagof<kTagBits>(lo2)); }
                 __syncwarp();
                 ri = false;
             }
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
-            const uint32_t mytag = tag4(v4);
+            const uint32_t mytag = tagof<kTagBits>(v4);
             bool tm = false;
-            if (live) tm = ((nt[key >> 3] >> ((key & 7u) * 4u)) & 15u) == mytag; else key = 0x10000u | lane;
+            if (live) tm = tag_get<kTagBits>(nt_sa, key) == mytag; else key = 0x10000u | lane;
             uint32_t pend = __ballot_sync(kFull, tm);
             uint32_t cnd = kInvalid, hits = 0;
             bool hit = false;
@@ -577,7 +634,7 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t
                 const uint32_t rest = pend & (pend - 1u), rest2 = rest & (rest - 1u);
                 const bool sel = ((pend & ~rest2) >> lane) & 1u;
                 if (sel) {
-                    cnd = tab_get<true>(tab, key);
+                    cnd = gpos_get(gtab, tab_off, key);
                     const bool chk = cnd != kInvalid && p - cnd <= 65535u;
                     hit = chk && view.ro4(chk ? cnd : 0u) == v4;
                 }
@@ -616,7 +673,7 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint16_t
             const uint32_t upto = partial ? w0 : (win < 32u ? win : width - 1u);
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
-            if (lane <= upto && (31u - __clz(mine)) == lane) { tab_put<true>(tab, key, p); nib_put(nt, key, mytag); }
+            if (lane <= upto && (31u - __clz(mine)) == lane) { gpos_put(gtab, tab_off, key, p); tag_put<kTagBits>(nt_sa, key, mytag); }
             __syncwarp();
             if (win < 32u) {
                 mpos = base + win * stride;
@@ -1036,20 +1093,27 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
     if (warp < (uint32_t)kS)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
-    else
+    else {
+#if ENC_TAB_OPAQUE
+        uint32_t toff = (blockIdx.x * kM + warp) * 4096u;          // opaque: not re-derived from blockIdx / threadIdx at every use
+        asm volatile("mov.b32 %0, %0;" : "+r"(toff));
+        matcher_loop<TabT, true>(a, tickets, gtab + toff, pr, lane);
+#else
         matcher_loop<TabT, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
+#endif
+    }
     retire_warp(tickets, gridDim.x * kM);
 }
 
-// Global position tables + shared-memory nibble tags (match_block_nib): kM matchers + kE emitters per CTA.
-// Blocks of at most 65 536 bytes, no dictionary.
-template <int kM, int kE>
-__global__ void __launch_bounds__((kM + kE) * 32, 2048 / ((kM + kE) * 32))
+// Global position tables + shared-memory tags (match_block_nib): kM matchers + kE emitters per CTA, kCtas CTAs per SM
+// (8 x 256 threads leave 32 registers per thread, 6 leave 40).  Blocks of at most 65 536 bytes, no dictionary.
+template <int kM, int kE, int kTagBits, int kCtas>
+__global__ void __launch_bounds__((kM + kE) * 32, kCtas)
 lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
 {
     constexpr int kR = kM / kE;
     static_assert(kM % kE == 0, "every emitter serves the same number of matchers");
-    __shared__ __align__(16) uint32_t nt_s[kM * 512];        // 4096 nibbles per matcher
+    __shared__ __align__(16) uint32_t nt_s[kM * 4096 * kTagBits / 32];
     __shared__ __align__(16) uint4 q_s[kM * 2 * kSeqBatchEntries];
     __shared__ uint32_t meta_s[kM * 8];
     __shared__ __align__(8) uint64_t bars_s[kM * 4];
@@ -1064,8 +1128,8 @@ lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
-    uint16_t *tab = gtab + ((size_t)blockIdx.x * kM + warp) * 4096;
-    uint32_t *nt = nt_s + warp * 512;
+    const uint32_t tab_off = opaque32((blockIdx.x * kM + warp) * 8192u);
+    const uint32_t nt_sa = opaque32(smem_addr(nt_s) + warp * (4096u * kTagBits / 8u));
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
         if (n > 65536u) continue;                                           // the u32 kernel's block
@@ -1077,7 +1141,7 @@ lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
         pr.block = b; pr.first = 1;
         WordView view(a.in + a.in_off[b]);
-        match_block_nib(view, n, tab, nt, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
+        match_block_nib<kTagBits>(view, n, reinterpret_cast<uint8_t *>(gtab), tab_off, nt_sa, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, lane);
     }
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0, lane);

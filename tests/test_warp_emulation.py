@@ -204,8 +204,11 @@ def test_lane_group_batches_keep_the_parse(name, data):
 # ---------------------------------------------------------------------------------------------------------------------
 # lz4_compress_blocks_gnib: 4-bit tags in SHARED memory beside the global position table, candidates verified first-K.
 # ---------------------------------------------------------------------------------------------------------------------
+_TAG_BITS = [4]                                                  # 4: nibble tags, 8: byte tags (gnib<.., 8, ..>)
+
+
 def _tag4(b, p):
-    return ((int.from_bytes(b[p:p + 4], "little") * 2246822519) & 0xFFFFFFFF) >> 28
+    return ((int.from_bytes(b[p:p + 4], "little") * 2246822519) & 0xFFFFFFFF) >> (32 - _TAG_BITS[0])
 
 
 def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 2) -> bytes:
@@ -248,7 +251,7 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
                 ntag[H(b, cur - 2)] = _tag4(b, cur - 2)
                 ri = False
             key = [H(b, p[i]) if live[i] else (0x10000 | i) for i in R]
-            mytag = [_tag4(b, p[i]) if live[i] else 16 for i in R]
+            mytag = [_tag4(b, p[i]) if live[i] else 256 for i in R]
             pend = [i for i in R if live[i] and ntag[key[i]] == mytag[i]]
             st["batches"] += 1
             hit = [False] * 32
@@ -330,10 +333,15 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
 
 @pytest.mark.parametrize("name,data", CASES, ids=[c[0] for c in CASES])
 def test_nibble_tags_first_k_keep_the_parse(name, data):
-    for K in (1, 2, 4):
-        assert warp_encode_nib(data, K=K) == oracle.compress_block(data)
-        assert warp_encode_nib(data, cont=True, h5=True, K=K) == oracle.compress_block_cont(data)
-        assert warp_encode_nib(data, cont=False, h5=True, K=K) == oracle.compress_block_fresh_h5(data)
+    for bits, ks in ((4, (1, 2, 4)), (8, (2,))):
+        _TAG_BITS[0] = bits
+        try:
+            for K in ks:
+                assert warp_encode_nib(data, K=K) == oracle.compress_block(data)
+                assert warp_encode_nib(data, cont=True, h5=True, K=K) == oracle.compress_block_cont(data)
+                assert warp_encode_nib(data, cont=False, h5=True, K=K) == oracle.compress_block_fresh_h5(data)
+        finally:
+            _TAG_BITS[0] = 4
 
 
 def test_nibble_tags_cut_the_table_and_candidate_traffic():

@@ -31,7 +31,8 @@ VARIANTS = {
     "warp_quarter": {"LZ4B200_ENC_G16": "871"},
     "warp_quarter62": {"LZ4B200_ENC_G16": "862", "LZ4B200_ENC_G16_CTAS": "6"},
     "warp_nib": {"LZ4B200_ENC_NIB": "1"},
-    "warp_nib6": {"LZ4B200_ENC_NIB": "1", "LZ4B200_ENC_NIB_CTAS": "6"},
+    "warp_nib6": {"LZ4B200_ENC_NIB": "3"},
+    "warp_tag8": {"LZ4B200_ENC_NIB": "2"},
 }
 
 
