@@ -522,13 +522,20 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         if (!a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
             // u16 entries: CTAs per SM x chains per CTA tables of 4096, one region per concurrently running launch
             const int g16_m = (ctx->enc_g16 % 100) / 10, g16_g = ctx->enc_g16 >= 800 ? 8 : 16;
-            const size_t chains_per_sm = ctx->enc_g16 ? (size_t)ctx->enc_g16_ctas * (32 / g16_g) * g16_m : 8u * 7u;
+            const size_t chains_per_sm = ctx->enc_g16 ? (size_t)ctx->enc_g16_ctas * (32 / g16_g) * g16_m : (ctx->enc_nib >= 4 ? 112u : 8u * 7u);
             const size_t region = (size_t)ctx->sm_count * chains_per_sm * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
             if (ctx->enc_nib && !ctx->enc_g16) {                                     // tags in shared memory: 1 = nibbles x 8 CTAs, 2 = bytes x 6 CTAs, 3 = nibbles x 6 CTAs (40 registers)
                 const uint32_t ctas = std::min(ctx->enc_nib_ctas, ctx->enc_nib == 1 ? 8 : 6);
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * ctas);
+                if (ctx->enc_nib == 4) {                                             // lane groups of 8 + 2-bit tags: 4 x 28 chains per SM
+                    const uint32_t g4 = std::min<uint32_t>((a.nblocks + 27) / 28, (uint32_t)ctx->sm_count * std::min(ctx->enc_nib_ctas, 4));
+                    lz4_compress_blocks_gtagg<8, 7, 1, 2, 4><<<g4, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtagg<8, 7, 1, 2, 4>";
+                } else if (ctx->enc_nib == 5) {                                      // lane groups of 16 + 2-bit tags: 8 x 14 chains per SM
+                    const uint32_t g5 = std::min<uint32_t>((a.nblocks + 13) / 14, (uint32_t)ctx->sm_count * std::min(ctx->enc_nib_ctas, 8));
+                    lz4_compress_blocks_gtagg<16, 7, 1, 2, 8><<<g5, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gtagg<16, 7, 1, 2, 8>";
+                } else
                 if (ctx->enc_nib == 2) { lz4_compress_blocks_gnib<7, 1, 8, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 8, 6>"; }
                 else if (ctx->enc_nib == 3) { lz4_compress_blocks_gnib<7, 1, 4, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 6>"; }
                 else { lz4_compress_blocks_gnib<7, 1, 4, 8><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 8>"; }

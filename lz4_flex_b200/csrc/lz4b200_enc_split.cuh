@@ -44,7 +44,10 @@
 
 namespace lz4b200 {
 
-constexpr uint32_t kSeqBatchEntries = 16;      // tuples per hand-off (two halves per pair)
+#ifndef ENC_SEQ_BATCH
+#define ENC_SEQ_BATCH 16   // tuples per hand-off (1..32): the emitter's cost per batch does not depend on it
+#endif
+constexpr uint32_t kSeqBatchEntries = ENC_SEQ_BATCH;      // tuples per hand-off (two halves per ring)
 constexpr uint32_t kWinBytes = 512;            // input look-ahead ring per pair: 4 lines of 128 bytes
 constexpr uint32_t kRingBytes = ENC_WINDOW ? kWinBytes : 0;   // shared memory actually reserved for it
 constexpr uint32_t kExitBlock = 0xffffffffu;
@@ -69,6 +72,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
+}
+// Producer-side wait for a free ring half.  One emitter serves 7 matchers, so a matcher finds its half still unread
+// every few batches; spinning there cost 2.46 G of the kernel's 16.6 G warp-instructions (YIELD / try_wait / BRA, 819 M
+// iterations — ncu source page of profiles/r2_ncu_summary.json's capture) in a kernel that is bound by instruction issue.
+// One immediate probe (the common case: already free), then try_wait with a suspend hint + nanosleep.
+#ifndef ENC_PROD_SLEEP_NS
+#define ENC_PROD_SLEEP_NS 200   // 0: spin (round-1 behaviour)
+#endif
+__device__ __forceinline__ void mbar_wait_producer(uint64_t *bar, uint32_t parity)
+{
+#if ENC_PROD_SLEEP_NS == 0
+    mbar_wait(bar, parity);
+#else
+    const uint32_t addr = smem_addr(bar);
+    uint32_t done;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    while (!done) {
+        __nanosleep(ENC_PROD_SLEEP_NS);
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(4u * ENC_PROD_SLEEP_NS) : "memory");
+    }
+#endif
 }
 // Consumer-side wait: the emitter is idle most of the time; spinning on try_wait would burn issue slots the
 // matchers need, so it backs off between polls.
@@ -107,7 +133,7 @@ struct SeqProducer {
         }
         k++; qn = 0; first = 0;
         // batch k goes into half k&1, last used by batch k-2: wait until the emitter has read it
-        if (k >= 2) mbar_wait(bars + 2 + (k & 1u), ((k >> 1) - 1u) & 1u);
+        if (k >= 2) mbar_wait_producer(bars + 2 + (k & 1u), ((k >> 1) - 1u) & 1u);
         __syncwarp();
     }
     __device__ __forceinline__ void push(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end, uint32_t lane)
@@ -540,9 +566,10 @@ __device__ __forceinline__ uint32_t tag_get(uint32_t nt_sa, uint32_t slot)
     if constexpr (kTagBits == 8) {
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(nt_sa + slot) : "memory");
         return v;
-    } else {
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nt_sa + ((slot >> 1) & ~3u)) : "memory");
-        return (v >> ((slot & 7u) * 4u)) & 15u;
+    } else {                                                     // 4- or 2-bit tags packed into 32-bit words
+        const uint32_t bit = slot * kTagBits;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nt_sa + ((bit >> 3) & ~3u)) : "memory");
+        return (v >> (bit & 31u)) & ((1u << kTagBits) - 1u);
     }
 }
 template <int kTagBits>
@@ -551,10 +578,14 @@ __device__ __forceinline__ void tag_put(uint32_t nt_sa, uint32_t slot, uint32_t 
     if constexpr (kTagBits == 8) {
         asm volatile("st.shared.u8 [%0], %1;" ::"r"(nt_sa + slot), "r"(tag) : "memory");
     } else {
-        const uint32_t sa = nt_sa + ((slot >> 1) & ~3u), sh = (slot & 7u) * 4u;
-        asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(sa), "r"(~(15u << sh)) : "memory");
+        const uint32_t bit = slot * kTagBits, sa = nt_sa + ((bit >> 3) & ~3u), sh = bit & 31u;
+        asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(sa), "r"(~(((1u << kTagBits) - 1u) << sh)) : "memory");
         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(tag << sh) : "memory");
     }
+}
+template <int kTagBits> __device__ __forceinline__ uint32_t tag_fill_word(uint32_t t)
+{
+    return kTagBits == 8 ? t * 0x01010101u : kTagBits == 4 ? t * 0x11111111u : t * 0x55555555u;
 }
 __device__ __forceinline__ uint32_t gpos_get(const uint8_t *gtab, uint32_t tab_off, uint32_t slot)
 {
@@ -585,7 +616,7 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint8_t 
         for (uint32_t i = lane; i < 4096u * 2u / 16u; i += 32)
             asm volatile("st.global.cg.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(t128 + i), "r"(f) : "memory");
         uint32_t lo0, hi0; view.ro5(0, lo0, hi0);               // an empty slot is a candidate at position 0: its tag
-        const uint32_t t = tagof<kTagBits>(lo0) * (kTagBits == 8 ? 0x01010101u : 0x11111111u);
+        const uint32_t t = tag_fill_word<kTagBits>(tagof<kTagBits>(lo0));
 #pragma unroll
         for (uint32_t i = lane; i < 4096u * kTagBits / 8u / 16u; i += 32)
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(nt_sa + i * 16u), "r"(t) : "memory");
@@ -1216,7 +1247,7 @@ struct SeqProducerG {                            // SeqProducer for a lane group
             mbar_arrive(bars + h);
         }
         k++; qn = 0; first = 0;
-        if (k >= 2) mbar_wait(bars + 2 + (k & 1u), ((k >> 1) - 1u) & 1u);
+        if (k >= 2) mbar_wait_producer(bars + 2 + (k & 1u), ((k >> 1) - 1u) & 1u);
         g.sync();
     }
     __device__ __forceinline__ void push(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end)
@@ -1416,6 +1447,228 @@ lz4_compress_blocks_gtabg(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
         pr.block = b; pr.first = 1;
         match_block_half<G>(a.in + a.in_off[b], n, tab, (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, g);
+    }
+    pr.block = kExitBlock; pr.first = 0;
+    pr.flush(0);
+    if (g.sub == 0) {
+        __threadfence();
+        if (atomicAdd(&tickets[1], 1u) == gridDim.x * kC - 1u) {
+            tickets[0] = 0;
+            tickets[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lane-group matcher with shared-memory tags (lz4_compress_blocks_gtagg): match_block_half's G-lane batches (32/G
+// chains per instruction stream: the cheapest instructions per sequence of all the matchers) + match_block_nib's tag
+// filter and first-2 verification (no speculative table / candidate traffic, which is what made 16 384 lane-group chains
+// thrash the L2).  Tags are 2 bits (1 KiB per chain) so that 112 chains per SM fit.  A batch covers probes
+// gi .. gi+G-1 of the current 32-probe step group and never crosses it.  Model: tests/test_warp_emulation.py::warp_encode_nib(G=..).
+// ---------------------------------------------------------------------------------------------
+template <int kG, int kTagBits>
+__device__ __forceinline__ void match_block_group_tag(const uint8_t *__restrict__ src, uint32_t n, uint8_t *gtab, uint32_t tab_off,
+                                                      uint32_t nt_sa, bool cont, bool h5, SeqProducerG<kG> &pr, const LaneGroup<kG> &g)
+{
+    constexpr uint32_t G = kG, kInvalid = 0xffffu, kAll = LaneGroup<kG>::kAll;
+    const uint32_t sub = g.sub, lt_mask = (1u << sub) - 1u;
+    if (n < 13) {                                               // compress.rs:343-346
+        pr.push_final(0, n);
+        return;
+    }
+    const WordView view(src);
+    {
+        const uint32_t f = cont ? 0xffffffffu : 0u;
+        uint4 *t128 = reinterpret_cast<uint4 *>(gtab + tab_off);
+#pragma unroll 4
+        for (uint32_t i = sub; i < 512u; i += G)
+            asm volatile("st.global.cg.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(t128 + i), "r"(f) : "memory");
+        uint32_t lo0, hi0; view.ro5(0, lo0, hi0);               // an empty slot is a candidate at position 0: its tag
+        const uint32_t t = tag_fill_word<kTagBits>(tagof<kTagBits>(lo0));
+#pragma unroll
+        for (uint32_t i = sub; i < 4096u * kTagBits / 8u / 16u; i += G)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(nt_sa + i * 16u), "r"(t) : "memory");
+        g.sync();
+    }
+    const uint32_t last_probe = n - 12, lim = n - 6;
+    uint32_t anchor = 0, cur = 0;
+    bool ri = false;                                            // T[H(cur-2)] = cur-2 still owed (compress.rs:460-461)
+    if (!cont) {                                                // compress.rs:353-359
+        uint32_t lo, hi; view.ro5(0, lo, hi);
+        const uint32_t s = h5 ? slot_h5(lo, hi) : slot_h4(lo);
+        if (sub == 0) { gpos_put(gtab, tab_off, s, 0u); tag_put<kTagBits>(nt_sa, s, tagof<kTagBits>(lo)); }
+        cur = 1;
+        g.sync();
+    }
+    for (;;) {                                                  // one sequence per iteration
+        uint32_t gbase = cur, stride = 1, gi = 0, cand, mpos;
+        for (;;) {                                              // probe batches: compress.rs:373-439
+            const uint32_t width = min(G, 32u - gi);
+            const uint32_t base = gbase + gi * stride;
+            const uint32_t p = base + sub * stride;
+            const bool act = sub < width;
+            const bool term = act && p > last_probe, live = act && !term;
+            uint32_t v4, hi;
+            view.ro5(live ? p : 0u, v4, hi);
+            if (ri) {
+                uint32_t lo2, hi2; view.ro5(cur - 2u, lo2, hi2);
+                const uint32_t s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
+                if (sub == 0) { gpos_put(gtab, tab_off, s2, cur - 2u); tag_put<kTagBits>(nt_sa, s2, tagof<kTagBits>(lo2)); }
+                g.sync();
+                ri = false;
+            }
+            uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
+            const uint32_t mytag = tagof<kTagBits>(v4);
+            bool tm = false;
+            if (live) tm = tag_get<kTagBits>(nt_sa, key) == mytag; else key = 0x10000u | sub;
+            uint32_t pend = g.ballot(tm);
+            uint32_t cnd = kInvalid, hits = 0;
+            bool hit = false;
+            while (pend) {                                      // verify the tag-matching probes two at a time, in order
+                const uint32_t rest = pend & (pend - 1u), rest2 = rest & (rest - 1u);
+                const bool sel = ((pend & ~rest2) >> sub) & 1u;
+                if (sel) {
+                    cnd = gpos_get(gtab, tab_off, key);
+                    const bool chk = cnd != kInvalid && p - cnd <= 65535u;
+                    hit = chk && view.ro4(chk ? cnd : 0u) == v4;
+                }
+                hits = g.ballot(sel && hit);
+                if (hits) break;
+                pend = rest2;
+            }
+            const uint32_t terms = (gbase + 31u * stride > last_probe) ? g.ballot(term) : 0u;
+            const uint32_t w0 = hits ? (uint32_t)__ffs(hits) - 1u : G;
+            const uint32_t upto0 = w0 < width ? w0 : width - 1u;
+            uint32_t same = 1u << sub, win = w0;
+            bool exact = w0 == 0u;
+            if (w0 >= 1u && w0 <= 3u) {
+                const uint32_t k0 = g.shfl(key, 0), k1 = g.shfl(key, 1), k2 = g.shfl(key, 2);
+                const bool clash = (sub >= 1u && key == k0) || (sub >= 2u && key == k1) || (sub >= 3u && key == k2);
+                exact = g.ballot(clash && sub <= w0) == 0u;
+            }
+            if (!exact) {
+                same = g.match_any(key);
+                const uint32_t prior = same & lt_mask;
+                const uint32_t le0 = (2u << upto0) - 1u;                     // upto0 <= G - 1 <= 15
+                if (g.ballot(prior != 0u) & le0) {
+                    const uint32_t pl = prior ? 31u - __clz(prior) : sub;    // the forwarded candidate is a probe of this
+                    const uint32_t pv = g.shfl(v4, pl);                      // batch: its 4 bytes sit in that lane's register
+                    if (prior) { cnd = base + pl * stride; hit = pv == v4; }
+                    const uint32_t h2 = g.ballot(hit) & le0;
+                    win = h2 ? (uint32_t)__ffs(h2) - 1u : G;
+                }
+            }
+            const bool partial = win == G && w0 < G;            // forwarding took the hit away: probes 0..w0 were executed
+            const uint32_t tfirst = terms ? (uint32_t)__ffs(terms) - 1u : G;
+            if (!partial && tfirst < win) {                     // compress.rs:381-384: the rest is literals
+                pr.push_final(anchor, n);
+                return;
+            }
+            const uint32_t upto = partial ? w0 : (win < G ? win : width - 1u);
+            const uint32_t mine = same & ((2u << upto) - 1u);
+            if (sub <= upto && (31u - __clz(mine)) == sub) { gpos_put(gtab, tab_off, key, p); tag_put<kTagBits>(nt_sa, key, mytag); }
+            g.sync();
+            if (win < G) {
+                mpos = base + win * stride;
+                cand = g.shfl(cnd, win);
+                break;
+            }
+            gi += upto + 1u;
+            if (gi == 32u) { gbase += 32u * stride; stride++; gi = 0; }
+        }
+        const uint32_t dist = mpos - cand;
+        // ---- extension: as match_block_half (forward in 4-byte words per lane, backward in bytes)
+        const uint32_t room = min(cand, mpos - anchor);
+        const bool inb = sub < room;
+        uint8_t b1 = 0, b2 = 1;
+        if (room) { b1 = view.byte(mpos - (inb ? 1u + sub : 0u)); b2 = view.byte(cand - (inb ? 1u + sub : 0u)); }
+        uint32_t end = mpos + 4u;
+        bool lim_stop;
+        for (;;) {
+            const uint32_t pos = end + 4u * sub;
+            const bool full = pos + 4u <= lim;                  // this lane's word lies before n - END_OFFSET
+            const uint32_t x = view.ro4(full ? pos : 0u) ^ view.ro4(full ? pos - dist : 0u);
+            const uint32_t nm = full ? (x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u) : 0u;
+            const uint32_t bad = g.ballot(nm < 4u);
+            if (bad) {
+                const uint32_t fl = (uint32_t)__ffs(bad) - 1u;
+                end += 4u * fl + g.shfl(nm, fl);
+                lim_stop = g.shfl(full ? 0u : 1u, fl) != 0u;    // stopped by the limit, not by a differing byte
+                break;
+            }
+            end += 4u * G;
+        }
+        uint32_t kb = 0;
+        if (room) {
+            const uint32_t bad = ~g.ballot(inb && b1 == b2) & kAll;
+            kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
+        }
+        if (lim_stop && end < lim) {                            // a word that crossed n - 6: at most 3 more bytes
+            const uint32_t q = end + sub;
+            const bool ok = sub < 4u && q < lim && view.byte(q < lim ? q : end) == view.byte((q < lim ? q : end) - dist);
+            end += (uint32_t)__ffs(~g.ballot(ok) & kAll) - 1u;
+        }
+        if (kb) {
+            mpos -= kb; cand -= kb;
+            while (kb == G) {                                   // more than G bytes backwards: rare
+                const uint32_t room2 = min(cand, mpos - anchor);
+                const bool inb2 = sub < room2;
+                const uint8_t c1 = view.byte(mpos - (inb2 ? 1u + sub : 0u)), c2 = view.byte(cand - (inb2 ? 1u + sub : 0u));
+                const uint32_t bad = ~g.ballot(inb2 && c1 == c2) & kAll;
+                kb = bad ? (uint32_t)__ffs(bad) - 1u : G;
+                mpos -= kb; cand -= kb;
+            }
+        }
+        pr.push(anchor, mpos, dist, end);
+        anchor = cur = end;
+        ri = true;
+    }
+}
+
+// kM matcher warps (32/G chains each) + kE emitter warps per CTA, kCtas CTAs per SM; per chain an 8 KiB u16 position
+// table in global memory and 4096 x kTagBits bits of tags in shared memory.
+template <int G, int kM, int kE, int kTagBits, int kCtas>
+__global__ void __launch_bounds__((kM + kE) * 32, kCtas)
+lz4_compress_blocks_gtagg(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
+{
+    constexpr int kC = (32 / G) * kM, kR = kC / kE;            // chains per CTA, rings per emitter
+    static_assert(kC % kE == 0, "every emitter serves the same number of chains");
+    __shared__ __align__(16) uint32_t nt_s[kC * 4096 * kTagBits / 32];
+    __shared__ __align__(16) uint4 q_s[kC * 2 * kSeqBatchEntries];
+    __shared__ uint32_t meta_s[kC * 8];
+    __shared__ __align__(8) uint64_t bars_s[kC * 4];
+    __shared__ EmitState st_s[kC];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x < (uint32_t)kC * 4u) mbar_init(bars_s + threadIdx.x, 1u);
+    __syncthreads();
+    if (warp >= (uint32_t)kM) {
+        const uint32_t e = warp - kM;
+        emit_loop_multi<kR>(a, q_s + e * kR * 2 * kSeqBatchEntries, meta_s + e * kR * 8, bars_s + e * kR * 4,
+                            st_s + e * kR, lane);
+        return;
+    }
+    const LaneGroup<G> g(lane);
+    const uint32_t chain = warp * (32u / G) + lane / G;
+    SeqProducerG<G> pr{q_s + chain * 2 * kSeqBatchEntries, meta_s + chain * 8, bars_s + chain * 4, 0u, 0u, 0u, 0u, g};
+    const uint32_t tab_off = opaque32((blockIdx.x * kC + chain) * 8192u);
+    const uint32_t nt_sa = opaque32(smem_addr(nt_s) + chain * (4096u * kTagBits / 8u));
+    for (;;) {
+        uint32_t b = 0;
+        if (g.sub == 0) b = atomicAdd(&tickets[0], 1u);
+        b = g.shfl(b, 0);
+        if (b >= a.nblocks) break;
+        const uint32_t n = a.in_len[b];
+        if (n > 65536u) continue;                               // blocks above 64 KiB belong to the u32-table kernel
+        const uint32_t fl = a.flags ? a.flags[b] : 0u;
+        if ((uint64_t)a.out_cap[b] < max_output_size_dev(n)) {              // compress.rs:338-340
+            if (g.sub == 0) { a.out_len[b] = 0; a.status[b] = LZ4B200_COMPRESS_OUTPUT_TOO_SMALL; }
+            continue;
+        }
+        const bool h5 = (fl & LZ4B200_BLOCK_HASH5_ALWAYS) || n >= 65535u;
+        pr.block = b; pr.first = 1;
+        match_block_group_tag<G, kTagBits>(a.in + a.in_off[b], n, reinterpret_cast<uint8_t *>(gtab), tab_off, nt_sa,
+                                           (fl & LZ4B200_BLOCK_CONT) != 0, h5, pr, g);
     }
     pr.block = kExitBlock; pr.first = 0;
     pr.flush(0);

@@ -74,7 +74,8 @@ elif MODE == "thread":
         run({"LZ4B200_THREAD_MIN": "1", "LZ4B200_ENC_THREAD_LANES": str(lanes), "LZ4B200_DEC_THREAD_LANES": str(lanes)}, f"thread kernels, {lanes} lanes/warp")
 elif MODE == "nib":
     run({}, "gtab 7+1 x8 (default)")
-    for mode, ctas, what in (("1", 8, "nibble tags, 32 regs"), ("3", 6, "nibble tags, 40 regs"), ("2", 6, "byte tags, 40 regs"), ("2", 5, "byte tags, 40 regs")):
+    for mode, ctas, what in (("2", 6, "byte tags, 32 lanes"), ("4", 4, "2-bit tags, 8-lane groups"), ("4", 3, "2-bit tags, 8-lane groups"),
+                             ("5", 8, "2-bit tags, 16-lane groups"), ("5", 6, "2-bit tags, 16-lane groups")):
         run({"LZ4B200_ENC_NIB": mode, "LZ4B200_ENC_NIB_CTAS": str(ctas)}, f"smem {what}, first-2 verify, {ctas} CTAs/SM", iters=4)
 elif MODE == "g16":
     run({}, "gtab 7+1 x8 (round 1 default)")

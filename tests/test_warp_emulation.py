@@ -211,7 +211,7 @@ def _tag4(b, p):
     return ((int.from_bytes(b[p:p + 4], "little") * 2246822519) & 0xFFFFFFFF) >> (32 - _TAG_BITS[0])
 
 
-def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 2) -> bytes:
+def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 2, G: int = 32) -> bytes:
     """Model of match_block_view<kNib>: every slot has a 4-bit tag of the 4 bytes at its position (shared memory); a probe
     whose tag disagrees cannot pass the 4-byte comparison (compress.rs:432-438), so it touches neither the position table
     nor the candidate.  The tag-matching probes of a batch are verified K at a time in probe order and the search stops at
@@ -237,11 +237,11 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
         tab[H(b, 0)] = 0
         ntag[H(b, 0)] = _tag4(b, 0)
         cur = 1
-    R = range(32)
+    R = range(G)                                                 # G < 32: a lane group of gtagg (32/G chains per warp)
     while True:
         gbase, stride, gi = cur, 1, 0
         while True:
-            width = 32 - gi
+            width = min(G, 32 - gi)                              # a batch never crosses the 32-probe step group
             p = [gbase + (gi + i) * stride for i in R]
             act = [i < width for i in R]
             term = [act[i] and p[i] > last_probe for i in R]
@@ -254,8 +254,8 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
             mytag = [_tag4(b, p[i]) if live[i] else 256 for i in R]
             pend = [i for i in R if live[i] and ntag[key[i]] == mytag[i]]
             st["batches"] += 1
-            hit = [False] * 32
-            cnd = [INVALID] * 32
+            hit = [False] * G
+            cnd = [INVALID] * G
 
             def verify(i):
                 c = tab[key[i]]
@@ -273,7 +273,7 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
                     hit[i] = verify(i)
                 if any(hit[i] for i in sel):
                     break
-            w0 = hit.index(True) if True in hit else 32
+            w0 = hit.index(True) if True in hit else G
             upto0 = min(w0, width - 1)
             exact = w0 == 0
             if 1 <= w0 <= 3:
@@ -290,21 +290,21 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
                             cnd[i] = p[prior[i][-1]]
                             hit[i] = b[cnd[i]:cnd[i] + 4] == b[p[i]:p[i] + 4]
                     hh = [hit[i] for i in range(upto0 + 1)]
-                    win = hh.index(True) if True in hh else 32
-            tfirst = term.index(True) if True in term else 32
-            if win == 32 and w0 < 32 and tfirst > w0:
+                    win = hh.index(True) if True in hh else G
+            tfirst = term.index(True) if True in term else G
+            if win == G and w0 < G and tfirst > w0:
                 # forwarding took the hit at w0 away and nothing before it matches: lanes 0..w0 were executed probes
                 upto = w0
                 st["partial"] += 1
             else:
                 if tfirst < win:                                 # compress.rs:381-384
                     return bytes(out) + _last_literals(b, anchor)
-                upto = win if win < 32 else width - 1
+                upto = win if win < G else width - 1
             for i in range(upto + 1):
                 if max(j for j in same[i] if j <= upto) == i:
                     tab[key[i]] = p[i]
                     ntag[key[i]] = mytag[i]
-            if win < 32:
+            if win < G:
                 mpos, cand = p[win], cnd[win]
                 break
             gi += upto + 1
@@ -333,13 +333,14 @@ def warp_encode_nib(b: bytes, cont: bool = False, h5=None, stats=None, K: int = 
 
 @pytest.mark.parametrize("name,data", CASES, ids=[c[0] for c in CASES])
 def test_nibble_tags_first_k_keep_the_parse(name, data):
-    for bits, ks in ((4, (1, 2, 4)), (8, (2,))):
+    for bits, ks, gs in ((4, (1, 2, 4), (32,)), (8, (2,), (32,)), (2, (2,), (8, 16))):
         _TAG_BITS[0] = bits
         try:
             for K in ks:
-                assert warp_encode_nib(data, K=K) == oracle.compress_block(data)
-                assert warp_encode_nib(data, cont=True, h5=True, K=K) == oracle.compress_block_cont(data)
-                assert warp_encode_nib(data, cont=False, h5=True, K=K) == oracle.compress_block_fresh_h5(data)
+                for G in gs:
+                    assert warp_encode_nib(data, K=K, G=G) == oracle.compress_block(data)
+                    assert warp_encode_nib(data, cont=True, h5=True, K=K, G=G) == oracle.compress_block_cont(data)
+                    assert warp_encode_nib(data, cont=False, h5=True, K=K, G=G) == oracle.compress_block_fresh_h5(data)
         finally:
             _TAG_BITS[0] = 4
 

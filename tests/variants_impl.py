@@ -33,6 +33,8 @@ VARIANTS = {
     "warp_nib": {"LZ4B200_ENC_NIB": "1"},
     "warp_nib6": {"LZ4B200_ENC_NIB": "3"},
     "warp_tag8": {"LZ4B200_ENC_NIB": "2"},
+    "warp_tagg8": {"LZ4B200_ENC_NIB": "4"},
+    "warp_tagg16": {"LZ4B200_ENC_NIB": "5"},
 }
 
 
