@@ -415,19 +415,35 @@ def run_ours(args):
     h_back = torch.empty(nb * BLOCK, dtype=torch.uint8).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
     e2e_t = []
+    call_t = []
     for it in range(2 + e2e_steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out, ooff, olen = block.compress_batch(h_in.numpy(), offs, lens, None, out=h_comp.numpy(), ctx=ctx)
+        t1 = time.perf_counter()
         block.decompress_batch(out, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= 2:
             e2e_t.append(dt)
+            call_t.append((t1 - t0, dt - (t1 - t0)))
     assert np.array_equal(h_back.numpy(), data)
     e2e_serial_s = float(np.mean(e2e_t))
+    # what the PCIe link of THIS rank delivers while every rank copies at once (pinned, 1 GiB each way): the floor of the step
+    link = {}
+    for name, fn in (("h2d", lambda: d_in.copy_(h_in, non_blocking=True)), ("d2h", lambda: h_back.copy_(d_back, non_blocking=True))):
+        ts = []
+        for it in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        link[name + "_gbs"] = round(nb * BLOCK / min(ts[1:]) / 1e9, 2)
 
     # The same two C-ABI calls, used the way a streaming caller would: the batch is cut into chunks, one host
     # thread compresses chunk c+1 (context A) while another decompresses chunk c (context B), so the H2D-heavy
@@ -559,7 +575,9 @@ def run_ours(args):
     per_rank = None
     if world > 1:
         # every rank's own e2e time and NUMA placement go into the record (which ranks are the slow ones, and where they sit)
-        mine = {"rank": rank, "e2e_ms": 1e3 * e2e_s, **numa_rec}
+        mine = {"rank": rank, "e2e_ms": round(1e3 * e2e_s, 2),
+                "compress_call_ms": round(1e3 * float(np.mean([c for c, _ in call_t])), 2),
+                "decompress_call_ms": round(1e3 * float(np.mean([d for _, d in call_t])), 2), **link, **numa_rec}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
         t = torch.tensor([e2e_s, e2e_serial_s], device=dev, dtype=torch.float64)
@@ -634,6 +652,8 @@ def run_ours(args):
         "e2e": {"value": world * mib_rank / e2e_s, "unit": "MiB/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
                 "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks, "per_rank": per_rank,
+                "compress_call_ms": 1e3 * float(np.mean([c for c, _ in call_t])),
+                "decompress_call_ms": 1e3 * float(np.mean([d for _, d in call_t])), "link": link,
                 "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers); "
                        + e2e_how},
         "gpu_launches": 2 * args.steps,

@@ -309,6 +309,24 @@ __device__ __forceinline__ void tab_fill16(uint4 *at, uint32_t f)
     else *at = make_uint4(f, f, f, f);
 }
 
+// Predicated forms for global u16 tables (ENC_PRED_TAB): `if (lane == 0) store` / `if (live) load` around inline asm compile
+// to a branch + BSSY/BSYNC + a divergence check before the next warp-level primitive (~6 instructions per site and
+// sequence); a predicated access is one.
+#ifndef ENC_PRED_TAB
+#define ENC_PRED_TAB 0
+#endif
+__device__ __forceinline__ void gtab16_put_if(bool pred, uint16_t *tab, uint32_t slot, uint32_t v)
+{
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.global.cg.u16 [%0], %1; }" ::"l"(tab + slot), "h"((uint16_t)v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t gtab16_get_if(bool pred, const uint16_t *tab, uint32_t slot, uint32_t dflt)
+{
+    uint16_t v = (uint16_t)dflt;
+    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p ld.global.cg.u16 %0, [%1]; }" : "+h"(v) : "l"(tab + slot), "r"((uint32_t)pred) : "memory");
+    return v;
+}
+template <typename TabT, bool kGT, bool kTag> constexpr bool kPredTab = ENC_PRED_TAB && kGT && !kTag && sizeof(TabT) == 2 && ENC_POLICY_HOIST == 2;
+
 // kTag (global u32 tables, blocks <= 64 KiB): an entry is (tag << 16) | position, tag = 16 bits hashed from the 4 bytes
 // at that position.  A probe fetches its candidate's bytes only when the tags agree — a tag mismatch proves the 4-byte
 // comparison of compress.rs:432-438 fails, so the parse is unchanged — which removes ~30 of the 32 speculative sector
@@ -379,7 +397,8 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
                 if (ENC_WINDOW) win.ro5(cur - 2u + win.mis, lo2, hi2); else view.ro5(cur - 2u, lo2, hi2);
                 s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
 #if !ENC_RI_PATCH
-                if (lane == 0) tab_put<kGT>(tab, s2, kTag ? ((cur - 2u) | (tag16(lo2) << 16)) : cur - 2u);
+                if constexpr (kPredTab<TabT, kGT, kTag>) gtab16_put_if(lane == 0, reinterpret_cast<uint16_t *>(tab), s2, cur - 2u);
+                else if (lane == 0) tab_put<kGT>(tab, s2, kTag ? ((cur - 2u) | (tag16(lo2) << 16)) : cur - 2u);
                 __syncwarp();
                 s2 = 0xffffffffu;
 #endif
@@ -387,7 +406,12 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
             }
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
             uint32_t cnd = kInvalid;
-            if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
+            if constexpr (kPredTab<TabT, kGT, kTag>) {
+                cnd = gtab16_get_if(live, reinterpret_cast<const uint16_t *>(tab), live ? key : 0u, kInvalid);
+                key = live ? key : (0x10000u | lane);
+            } else {
+                if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
+            }
             const uint32_t mytag = kTag ? tag16(v4) : 0u;
             bool tag_ok = true;
             if (kTag) { tag_ok = cnd != kInvalid && (cnd >> 16) == mytag; if (cnd != kInvalid) cnd &= 0xffffu; }
@@ -450,7 +474,9 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
             const uint32_t upto = win < 32u ? win : width - 1u;
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
-            if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, kTag ? (p | (mytag << 16)) : p);
+            if constexpr (kPredTab<TabT, kGT, kTag>)
+                gtab16_put_if(lane <= upto && (31u - __clz(mine)) == lane, reinterpret_cast<uint16_t *>(tab), key & 0xfffu, p);
+            else if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, kTag ? (p | (mytag << 16)) : p);
 #if ENC_RI_PATCH
             if (s2 != 0xffffffffu) {                            // uniform: first batch after a match
                 const uint32_t dups = __ballot_sync(kFull, key == s2 && lane <= upto);
