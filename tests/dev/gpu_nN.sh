@@ -10,5 +10,6 @@ python - <<PY
 import json
 d = json.loads(open('gpurun_out/bench_n$N.json').read().strip().splitlines()[-1])
 print('N=$N value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['numa'])
+print('per_rank', json.dumps(d['e2e'].get('per_rank')))
 f = d['sharded_frame']; print('frame', f['value'], f['ms_per_step'], f['collective'], f['parity'], f['e2e'])
 PY
