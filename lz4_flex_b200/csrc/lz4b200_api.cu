@@ -264,7 +264,7 @@ struct lz4b200_ctx {
     const uint32_t *pipe_tickets = nullptr;  // base of the host pipeline's ticket blocks (selects a table region)
     int enc_g16 = 0;                          // LZ4B200_ENC_G16=62|71 (16-lane groups) or 862|871 (8-lane groups): lane-group matchers, 0: off
     int enc_g16_ctas = 8;                     // LZ4B200_ENC_G16_CTAS
-    int enc_nib = 0;                          // LZ4B200_ENC_NIB=1: shared-memory nibble tags + first-2 verification (gnib)
+    int enc_nib = 0;                          // (A/B build) LZ4B200_ENC_NIB=1..5: shared-memory tags + first-2 verification (gnib / gtagg)
     int enc_nib_ctas = 8;                     // LZ4B200_ENC_NIB_CTAS
     // K1-S2 (one chain per CTA over the TMA-fed ring, lz4b200_solo_kernel.cuh): LZ4B200_ENC_SOLO=2 routes batches of
     // blocks > 64 KiB (and batches of at most enc_solo_small_max small blocks) to it
@@ -522,10 +522,11 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
         if (!a.dict_len && a.nblocks > (uint32_t)ctx->sm_count * 24u) {
             // u16 entries: CTAs per SM x chains per CTA tables of 4096, one region per concurrently running launch
             const int g16_m = (ctx->enc_g16 % 100) / 10, g16_g = ctx->enc_g16 >= 800 ? 8 : 16;
-            const size_t chains_per_sm = ctx->enc_g16 ? (size_t)ctx->enc_g16_ctas * (32 / g16_g) * g16_m : (ctx->enc_nib >= 4 ? 112u : 8u * 7u);
+            const size_t chains_per_sm = ctx->enc_g16 ? (size_t)ctx->enc_g16_ctas * (32 / g16_g) * g16_m : (ctx->enc_nib >= 4 ? 112u : 8u * 7u);   // enc_nib: A/B build only
             const size_t region = (size_t)ctx->sm_count * chains_per_sm * 4096u;
             if (!ctx->check(ctx->d_gtab16.reserve(region * 9u), "gtab")) return LZ4B200_CUDA_ERROR;
             uint16_t *gt = ctx->d_gtab16.p + table_slot(ctx, tickets) * region;
+#ifdef LZ4B200_AB_VARIANTS
             if (ctx->enc_nib && !ctx->enc_g16) {                                     // tags in shared memory: 1 = nibbles x 8 CTAs, 2 = bytes x 6 CTAs, 3 = nibbles x 6 CTAs (40 registers)
                 const uint32_t ctas = std::min(ctx->enc_nib_ctas, ctx->enc_nib == 1 ? 8 : 6);
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + 6) / 7, (uint32_t)ctx->sm_count * ctas);
@@ -539,7 +540,9 @@ lz4b200_status launch_compress(lz4b200_ctx *ctx, const BatchArgs &args, uint32_t
                 if (ctx->enc_nib == 2) { lz4_compress_blocks_gnib<7, 1, 8, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 8, 6>"; }
                 else if (ctx->enc_nib == 3) { lz4_compress_blocks_gnib<7, 1, 4, 6><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 6>"; }
                 else { lz4_compress_blocks_gnib<7, 1, 4, 8><<<grid, 256, 0, s>>>(a, tickets + 2, gt); ctx->last_kernel[0] = "lz4_compress_blocks_gnib<7, 1, 4, 8>"; }
-            } else if (ctx->enc_g16) {                                               // 2 or 4 chains per matcher warp
+            } else
+#endif
+            if (ctx->enc_g16) {                                               // 2 or 4 chains per matcher warp
                 const int m = (ctx->enc_g16 % 100) / 10, gsz = ctx->enc_g16 >= 800 ? 8 : 16;   // 62 | 71 (G = 16), 862 | 871 (G = 8)
                 const int per_cta = (32 / gsz) * m;
                 const uint32_t grid = std::min<uint32_t>((a.nblocks + per_cta - 1) / per_cta, (uint32_t)(ctx->sm_count * ctx->enc_g16_ctas));
@@ -684,8 +687,10 @@ lz4b200_status lz4b200_ctx_create(int device, lz4b200_ctx **out)
     }
     if (const char *g = getenv("LZ4B200_ENC_G16")) ctx->enc_g16 = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_G16_CTAS")) ctx->enc_g16_ctas = std::max(1, std::min(8, atoi(g)));
+#ifdef LZ4B200_AB_VARIANTS
     if (const char *g = getenv("LZ4B200_ENC_NIB")) ctx->enc_nib = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_NIB_CTAS")) ctx->enc_nib_ctas = std::max(1, std::min(8, atoi(g)));
+#endif
     if (const char *g = getenv("LZ4B200_ENC_SOLO")) ctx->enc_solo = atoi(g);
     if (const char *g = getenv("LZ4B200_ENC_SOLO_SMALL_MAX")) ctx->enc_solo_small_max = (uint32_t)atoll(g);
     if (ctx->enc_solo2_ctas_per_sm < 1 && ctx->enc_solo == 2) ctx->enc_solo = 0;

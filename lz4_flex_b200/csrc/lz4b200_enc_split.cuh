@@ -44,9 +44,6 @@
 
 namespace lz4b200 {
 
-#ifndef ENC_PUSH_SA
-#define ENC_PUSH_SA 0      // build-time A/B: tuple stores through an opaque shared address (SeqProducer::arm)
-#endif
 #ifndef ENC_SEQ_BATCH
 #define ENC_SEQ_BATCH 16   // tuples per hand-off (1..32): the emitter's cost per batch does not depend on it
 #endif
@@ -124,26 +121,6 @@ struct SeqProducer {
     uint32_t qn;              // tuples in the current half
     uint32_t block;
     uint32_t first;
-    uint32_t q_sa = 0;        // ENC_PUSH_SA: shared-space address of q, opaque to the compiler (see arm())
-
-    // ENC_PUSH_SA = 1: push() stores through a 32-bit shared address kept in a register instead of a generic pointer the
-    // compiler re-derives from threadIdx at every sequence (S2R / S2UR / ULEA / LEA ... around the lane-0 STS.128).
-    __device__ __forceinline__ void arm()
-    {
-#if ENC_PUSH_SA
-        q_sa = smem_addr(q);
-        asm volatile("mov.b32 %0, %0;" : "+r"(q_sa));
-#endif
-    }
-    __device__ __forceinline__ void put_tuple(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t lane)
-    {
-#if ENC_PUSH_SA
-        asm volatile("{ .reg .pred p; setp.eq.u32 p, %5, 0; @p st.shared.v4.u32 [%0], {%1, %2, %3, %4}; }"
-                     ::"r"(q_sa + (((k & 1u) * kSeqBatchEntries + qn) << 4)), "r"(x), "r"(y), "r"(z), "r"(w), "r"(lane) : "memory");
-#else
-        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(x, y, z, w);
-#endif
-    }
 
     __device__ __forceinline__ void flush(uint32_t last, uint32_t lane)
     {
@@ -161,14 +138,14 @@ struct SeqProducer {
     }
     __device__ __forceinline__ void push(uint32_t anchor, uint32_t mpos, uint32_t dist, uint32_t end, uint32_t lane)
     {
-        put_tuple(anchor, mpos, dist, end, lane);
+        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, mpos, dist, end);
         qn++;
         if (qn == kSeqBatchEntries) flush(0, lane);
     }
     // the last tuple of a block (literals only): hand the batch over with the "last" flag
     __device__ __forceinline__ void push_final(uint32_t anchor, uint32_t n, uint32_t lane)
     {
-        put_tuple(anchor, 0u, 0u, n, lane);
+        if (lane == 0) q[(k & 1u) * kSeqBatchEntries + qn] = make_uint4(anchor, 0u, 0u, n);
         qn++;
         flush(1, lane);
     }
@@ -559,6 +536,7 @@ __device__ __forceinline__ void match_block(const uint8_t *__restrict__ src, uin
     match_block_view<TabT, kGT, kTag>(view, n, tab, ring, cont, h5, pr, lane);
 }
 
+#ifdef LZ4B200_AB_VARIANTS   // measured and rejected: A/B build only
 // ---------------------------------------------------------------------------------------------
 // Matcher with 4-bit tags in SHARED memory beside the global position table (lz4_compress_blocks_gnib).
 // What `gtab` pays for its 56 chains per SM is table and candidate traffic: every probe batch loads 32 table entries
@@ -792,6 +770,8 @@ __device__ __forceinline__ void match_block_nib(View &view, uint32_t n, uint8_t 
         ri = true;
     }
 }
+
+#endif  // LZ4B200_AB_VARIANTS (shared-memory tag matcher)
 
 // ---------------------------------------------------------------------------------------------
 // matcher with an external dictionary: compress_into_with_dict (compress.rs:554-583, 610-616).
@@ -1076,7 +1056,6 @@ lz4_compress_blocks_split(BatchArgs a, uint32_t *tickets)
     }
     constexpr bool kSmall = sizeof(TabT) == 2;
     SeqProducer pr{q, meta, bars, 0u, 0u, 0u, 0u};
-    pr.arm();
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
         const uint64_t span = (uint64_t)n + (kDict ? a.dict_len : 0u);      // table layout follows dict + input: compress.rs:559
@@ -1146,7 +1125,6 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
-    pr.arm();
     if (warp < (uint32_t)kS)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
     else {
@@ -1161,6 +1139,7 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
     retire_warp(tickets, gridDim.x * kM);
 }
 
+#ifdef LZ4B200_AB_VARIANTS
 // Global position tables + shared-memory tags (match_block_nib): kM matchers + kE emitters per CTA, kCtas CTAs per SM
 // (8 x 256 threads leave 32 registers per thread, 6 leave 40).  Blocks of at most 65 536 bytes, no dictionary.
 template <int kM, int kE, int kTagBits, int kCtas>
@@ -1184,7 +1163,6 @@ lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
-    pr.arm();
     const uint32_t tab_off = opaque32((blockIdx.x * kM + warp) * 8192u);
     const uint32_t nt_sa = opaque32(smem_addr(nt_s) + warp * (4096u * kTagBits / 8u));
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
@@ -1204,6 +1182,8 @@ lz4_compress_blocks_gnib(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
     pr.flush(0, lane);
     retire_warp(tickets, gridDim.x * kM);
 }
+
+#endif  // LZ4B200_AB_VARIANTS (gnib kernel)
 
 #ifdef LZ4B200_AB_VARIANTS
 // Tagged global tables (kTag, see match_block): kM matchers + kE emitters per CTA, 16 KiB of (tag, position) entries per
@@ -1228,7 +1208,6 @@ lz4_compress_blocks_gtag(BatchArgs a, uint32_t *tickets, uint32_t *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
-    pr.arm();
     matcher_loop<uint32_t, true, true>(a, tickets, gtab + ((size_t)blockIdx.x * kM + warp) * 4096, pr, lane);
     retire_warp(tickets, gridDim.x * kM);
 }
@@ -1487,6 +1466,7 @@ lz4_compress_blocks_gtabg(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
     }
 }
 
+#ifdef LZ4B200_AB_VARIANTS   // measured and rejected: A/B build only
 // ---------------------------------------------------------------------------------------------
 // Lane-group matcher with shared-memory tags (lz4_compress_blocks_gtagg): match_block_half's G-lane batches (32/G
 // chains per instruction stream: the cheapest instructions per sequence of all the matchers) + match_block_nib's tag
@@ -1708,6 +1688,8 @@ lz4_compress_blocks_gtagg(BatchArgs a, uint32_t *tickets, uint16_t *gtab)
         }
     }
 }
+
+#endif  // LZ4B200_AB_VARIANTS (gtagg)
 
 template <typename TabT, int kPairs>
 constexpr size_t split_smem_bytes() { return (size_t)kPairs * (4096 * sizeof(TabT) + 2 * kSeqBatchEntries * 16 + kRingBytes + 32 + 32); }

@@ -247,7 +247,6 @@ lz4_compress_blocks_solo2(BatchArgs a, uint32_t *tickets)
     WarpRingView view;
     view.ring = ring; view.ring32 = reinterpret_cast<const uint32_t *>(ring); view.bars = rbars; view.phases = 0u;
     SeqProducer pr{q, meta, bars, 0u, 0u, 0u, 0u};
-    pr.arm();
     for (uint32_t b = next_ticket(tickets); b < a.nblocks; b = next_ticket(tickets)) {
         const uint32_t n = a.in_len[b];
         const uint32_t fl = a.flags ? a.flags[b] : 0u;
