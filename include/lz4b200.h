@@ -110,7 +110,10 @@ const char *lz4b200_ctx_last_kernel(const lz4b200_ctx *ctx, int which);
 size_t lz4b200_max_output_size(size_t input_len);
 
 /* ---- block API, one block, host pointers -------------------------------------------------
- * 1:1 replacements; PCIe-bound by construction.  Use the batch calls for throughput. */
+ * 1:1 replacements.  One call = one block = ONE serial parse chain on the GPU: a 64 KiB block costs >= 2.6 ms to
+ * compress and ~1 ms to decompress however empty the machine is (a CPU core needs 40 us / 15 us) — these calls are
+ * chain-latency-bound, not PCIe-bound.  They exist for drop-in completeness; throughput comes from the batch calls,
+ * which run thousands of such chains at once ("Which call"). */
 
 /* block::compress_into — src/block/compress.rs:599-601.  Fails up-front with
  * COMPRESS_OUTPUT_TOO_SMALL when cap < lz4b200_max_output_size(n) (compress.rs:338-340). */
