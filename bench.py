@@ -11,7 +11,11 @@ frame-mode gather of compressed chunks is measured separately with --workload fr
 
 value      = uncompressed MiB per second of the whole job (all ranks) over the compress+decompress step,
              inputs resident in HBM, timed with CUDA events, max over ranks.
-e2e        = the same metric through the host-pointer C-ABI calls, H2D/D2H copies inside the timed region.
+e2e        = the same metric through the host-pointer C-ABI calls, H2D/D2H copies inside the timed region, measured two
+             ways and both reported: one step at a time (compress call, then decompress call), and as a stream of batches
+             (compress of batch k on one thread / context next to decompress of batch k-1 on another: the two calls use
+             opposite directions of the PCIe link; K batches timed including fill and drain).  `e2e.value` is the better
+             one and `e2e.mode` names it.
 roofline   = dominant kernel (compress) against the measured HBM copy peak; the decompress kernel's roofline is
              reported beside it.
 cpu_baseline = the C oracle (a restatement of lz4_flex's algorithm; Rust is not available) on the host cores.
@@ -462,6 +466,21 @@ def run_ours(args):
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
         link[name + "_gbs"] = round(nb * BLOCK / min(ts[1:]) / 1e9, 2)
+    # both directions at once (two streams): what a perfectly overlapped compress + decompress pipeline could count on
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    ts = []
+    for it in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            h_back.copy_(d_back, non_blocking=True)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    link["duplex_gbs_each_way"] = round(nb * BLOCK / min(ts[1:]) / 1e9, 2)
 
     # The same two C-ABI calls, used the way a streaming caller would: the batch is cut into chunks, one host
     # thread compresses chunk c+1 (context A) while another decompresses chunk c (context B), so the H2D-heavy
@@ -590,10 +609,113 @@ def run_ours(args):
             print(f"# e2e {kind} {cfg}: {1e3 * float(np.mean(ts)):.2f} ms (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
     pool_ctx.clear()
     h_comp_slots = None
+
+    # ---- a STREAM of batches through the same two calls: while batch k is compressed (thread A, context 1: 1 GiB up, 0.25 GiB
+    # down) batch k-1 is decompressed (thread B, context 2: 0.25 GiB up, 1 GiB down).  Every batch still makes the whole trip
+    # host -> compress -> host -> decompress -> host; the two calls of one tick use opposite directions of the duplex link
+    # and no call is cut into chunks (no extra tails).  Timed over K batches INCLUDING the fill and drain ticks (K + 1 ticks).
+    h_comp2 = torch.empty(comp_bytes + 4096, dtype=torch.uint8).pin_memory()
+
+    def stream(K):
+        bufs = [h_comp.numpy(), h_comp2.numpy()]
+        res = [None, None]
+        err = []
+
+        def comp(k):
+            try:
+                res[k & 1] = block.compress_batch(h_in.numpy(), offs, lens, None, out=bufs[k & 1], ctx=ctx)
+            except Exception as e:                      # noqa: BLE001
+                err.append(e)
+
+        for k in range(K + 1):
+            th = None
+            if k < K:
+                th = threading.Thread(target=comp, args=(k,))
+                th.start()
+            if k >= 1:
+                o, ooff, olen = res[(k - 1) & 1]
+                block.decompress_batch(o, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx2)
+            if th is not None:
+                th.join()
+            if err:
+                raise err[0]
+
+    # The same stream with free-running workers: `nc` compress threads (one context each) take batches from a queue — the
+    # tail of one compress call (one block's chain + read-back, the H2D link idle) overlaps the next call's copy — and one
+    # decompress thread follows through a queue of finished batches.  Compressed outputs live in a ring of pinned buffers.
+    stream_ctx = {}
+    ring = [h_comp, h_comp2] + [torch.empty(comp_bytes + 4096, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def stream2(K, nc):
+        todo, done, free = _queue.Queue(), _queue.Queue(), _queue.Queue()
+        for k in range(K):
+            todo.put(k)
+        for b in ring:
+            free.put(b)
+        err = []
+
+        def cw(i):
+            c = ctx if i == 0 else stream_ctx.setdefault(i, block.Context(local))
+            try:
+                while True:
+                    try:
+                        todo.get_nowait()
+                    except _queue.Empty:
+                        break
+                    buf = free.get()
+                    done.put((buf, block.compress_batch(h_in.numpy(), offs, lens, None, out=buf.numpy(), ctx=c)))
+            except Exception as e:                      # noqa: BLE001
+                err.append(e)
+
+        cws = [threading.Thread(target=cw, args=(i,)) for i in range(nc)]
+        for t in cws:
+            t.start()
+        for _ in range(K):
+            buf, (o, ooff, olen) = done.get()
+            block.decompress_batch(o, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx2)
+            free.put(buf)
+        for t in cws:
+            t.join()
+        if err:
+            raise err[0]
+
+    stream_rec = None
+    if nb >= 4096:
+        K = 2 * e2e_steps
+        stream_s, stream_how = 1e30, ""
+        for label, fn in (("tick", lambda: stream(K)), ("free-running, 1 compress thread", lambda: stream2(K, 1)),
+                          ("free-running, 2 compress threads", lambda: stream2(K, 2))):
+            ts = []
+            for it in range(3):
+                h_back.numpy()[::4096] = 0
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) / K)
+                assert np.array_equal(h_back.numpy(), data)
+            if rank == 0 and os.environ.get("LZ4B200_DEBUG"):
+                print(f"# e2e stream ({label}) of {K} batches: {1e3 * min(ts[1:]):.2f} ms per batch", file=sys.stderr)
+            if min(ts[1:]) < stream_s:
+                stream_s, stream_how = float(min(ts[1:])), label
+        stream_ctx.clear()
+        stream_local = stream_s
+        if world > 1:
+            t = torch.tensor([stream_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            stream_s = float(t.cpu()[0])
+        stream_rec = {"value": world * (nb * BLOCK / 2**20) / stream_s, "unit": "MiB/s", "ms_per_batch": 1e3 * stream_s, "batches": K,
+                      "how": f"compress(batch k) on its own host thread(s) / context(s) while earlier batches are decompressed on "
+                             f"another ({stream_how}); {K} batches timed including fill and drain; every batch makes the whole round trip"}
+        if rank == 0 and os.environ.get("LZ4B200_DEBUG"):
+            print(f"# e2e stream of {K} batches: {1e3 * stream_s:.2f} ms per batch (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
+    del h_comp2, ring
     per_rank = None
     if world > 1:
         # every rank's own e2e time and NUMA placement go into the record (which ranks are the slow ones, and where they sit)
-        mine = {"rank": rank, "e2e_ms": round(1e3 * e2e_s, 2),
+        mine = {"rank": rank, "e2e_ms": round(1e3 * e2e_s, 2), "stream_ms": round(1e3 * stream_local, 2) if stream_rec else None,
                 "compress_call_ms": round(1e3 * float(np.mean([c for c, _ in call_t])), 2),
                 "decompress_call_ms": round(1e3 * float(np.mean([d for _, d in call_t])), 2), **link, **numa_rec}
         per_rank = [None] * world
@@ -670,13 +792,18 @@ def run_ours(args):
             "single_thread": {"compress_mibs": cpu_one["compress_mibs"],
                               "decompress_mibs": cpu_one["decompress_mibs"]},
             "liblz4_anchor": liblz4_anchor(data, min(nb, 1024))},
-        "e2e": {"value": world * mib_rank / e2e_s, "unit": "MiB/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s,
+        # headline = the better of (a) one compress call then one decompress call per step, (b) the stream of batches in which
+        # the two calls of consecutive steps share the duplex link; both are in the record, `mode` says which one `value` is
+        "e2e": {"value": world * mib_rank / min(e2e_s, stream_s if stream_rec else 1e30), "unit": "MiB/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * min(e2e_s, stream_s if stream_rec else 1e30),
+                "mode": "stream of batches" if (stream_rec and stream_s < e2e_s) else "one step at a time",
+                "one_step_at_a_time": {"value": world * mib_rank / e2e_s, "ms_per_step": 1e3 * e2e_s},
                 "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks, "per_rank": per_rank,
                 "compress_call_ms": 1e3 * float(np.mean([c for c, _ in call_t])),
-                "decompress_call_ms": 1e3 * float(np.mean([d for _, d in call_t])), "link": link,
+                "decompress_call_ms": 1e3 * float(np.mean([d for _, d in call_t])), "link": link, "stream": stream_rec,
                 "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers); "
-                       + e2e_how},
+                       + (stream_rec["how"] if (stream_rec and stream_s < e2e_s) else e2e_how)},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
         "numa": numa_rec,
