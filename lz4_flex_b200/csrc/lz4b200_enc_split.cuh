@@ -1125,7 +1125,7 @@ lz4_compress_blocks_gtab(BatchArgs a, uint32_t *tickets, TabT *gtab)
         return;
     }
     SeqProducer pr{q_s + warp * 2 * kSeqBatchEntries, meta_s + warp * 8, bars_s + warp * 4, 0u, 0u, 0u, 0u};
-    if (warp < (uint32_t)kS)
+    if (kS > 0 && warp + 1u <= (uint32_t)kS)
         matcher_loop<TabT, false>(a, tickets, reinterpret_cast<TabT *>(smem_raw) + warp * 4096, pr, lane);
     else {
 #if ENC_TAB_OPAQUE
