@@ -642,7 +642,7 @@ def run_ours(args):
 
     stream_rec = None
     if nb >= 4096:
-        K = 2 * e2e_steps
+        K = 4 * e2e_steps                               # 20 batches by default: fill + drain add one tick to K
         # (free-running variants — no join per tick, one or two compress threads — were slower at N=1, 39.8-41.4 ms vs 37.6,
         # and the two-compress-thread one once handed the decoder an incomplete buffer at N=8: not kept.)
         ts = []
