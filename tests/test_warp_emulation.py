@@ -368,3 +368,31 @@ def test_nibble_partial_batches_happen():
             assert warp_encode_nib(x, stats=s) == oracle.compress_block(x)
             partial += s["partial"]
     assert partial >= 5, partial
+
+
+def test_tag_scheme_on_random_structured_inputs():
+    """Property check of the shared-memory-tag scheme (all tag widths, warp and lane-group batches) on seeded random inputs
+    built to collide: tiny alphabets, word soup, long runs with single-byte defects."""
+    rng = np.random.default_rng(20240923)
+    for trial in range(24):
+        kind = trial % 3
+        n = int(rng.integers(13, 9000))
+        if kind == 0:
+            data = rng.integers(0, int(rng.integers(2, 30)), n, dtype=np.uint8).tobytes()
+        elif kind == 1:
+            words = [rng.integers(0, 256, int(rng.integers(3, 9)), dtype=np.uint8).tobytes() for _ in range(int(rng.integers(4, 200)))]
+            data = b"".join(words[int(i)] for i in rng.integers(0, len(words), n // 4 + 1))[:n]
+        else:
+            base = bytearray(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8).tobytes() * (n // 2 + 1))[:n]
+            for _ in range(int(rng.integers(0, 12))):
+                base[int(rng.integers(0, n))] ^= 0x55
+            data = bytes(base)
+        want = (oracle.compress_block(data), oracle.compress_block_cont(data), oracle.compress_block_fresh_h5(data))
+        for bits, G in ((2, 8), (2, 16), (4, 32), (8, 32)):
+            _TAG_BITS[0] = bits
+            try:
+                assert warp_encode_nib(data, G=G) == want[0], (trial, bits, G)
+                assert warp_encode_nib(data, cont=True, h5=True, G=G) == want[1], (trial, bits, G)
+                assert warp_encode_nib(data, cont=False, h5=True, G=G) == want[2], (trial, bits, G)
+            finally:
+                _TAG_BITS[0] = 4
