@@ -632,40 +632,54 @@ def run_ours(args):
             if k < K:
                 th = threading.Thread(target=comp, args=(k,))
                 th.start()
-            if k >= 1:
-                o, ooff, olen = res[(k - 1) & 1]
-                block.decompress_batch(o, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx2)
-            if th is not None:
-                th.join()
+            try:
+                if k >= 1:
+                    o, ooff, olen = res[(k - 1) & 1]
+                    block.decompress_batch(o, ooff, olen, h_back.numpy(), offs, lens, ctx=ctx2)
+            finally:
+                if th is not None:
+                    th.join()                               # never leave the compress thread running on `ctx`
             if err:
                 raise err[0]
 
-    stream_rec = None
+    stream_rec, stream_failed = None, None
     if nb >= 4096:
         K = 4 * e2e_steps                               # 20 batches by default: fill + drain add one tick to K
         # (free-running variants — no join per tick, one or two compress threads — were slower at N=1, 39.8-41.4 ms vs 37.6,
         # and the two-compress-thread one once handed the decoder an incomplete buffer at N=8: not kept.)
-        ts = []
-        for it in range(3):
+        ts, stream_err = [], None
+        for it in range(3):                                 # a failure on one rank must not leave the others in a collective
             h_back.numpy()[::4096] = 0
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            stream(K)
-            torch.cuda.synchronize()
-            ts.append((time.perf_counter() - t0) / K)
-            assert np.array_equal(h_back.numpy(), data)
+            try:
+                stream(K)
+                torch.cuda.synchronize()
+                ts.append((time.perf_counter() - t0) / K)
+                if not np.array_equal(h_back.numpy(), data):
+                    stream_err = "round trip differs from the input"
+            except Exception as e:                          # noqa: BLE001
+                stream_err = f"{type(e).__name__}: {e}"
+                ts.append(1e30)
         stream_s, stream_how = float(min(ts[1:])), "both calls joined per tick"
         stream_local = stream_s
+        ok = 0.0 if stream_err else 1.0
         if world > 1:
-            t = torch.tensor([stream_s], device=dev, dtype=torch.float64)
+            t = torch.tensor([stream_s, -ok], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            stream_s = float(t.cpu()[0])
-        stream_rec = {"value": world * (nb * BLOCK / 2**20) / stream_s, "unit": "MiB/s", "ms_per_batch": 1e3 * stream_s, "batches": K,
-                      "how": f"compress(batch k) on its own host thread(s) / context(s) while earlier batches are decompressed on "
-                             f"another ({stream_how}); {K} batches timed including fill and drain; every batch makes the whole round trip"}
-        if rank == 0 and os.environ.get("LZ4B200_DEBUG"):
+            stream_s, ok = float(t.cpu()[0]), -float(t.cpu()[1])
+        if ok < 1.0:                                        # reported, never counted
+            stream_rec, stream_s = None, 1e30
+            stream_failed = stream_err or "failed on another rank"
+            print(f"# rank {rank}: e2e stream mode failed: {stream_failed}", file=sys.stderr)
+        else:
+            stream_failed = None
+            stream_rec = {"value": world * (nb * BLOCK / 2**20) / stream_s, "unit": "MiB/s", "ms_per_batch": 1e3 * stream_s, "batches": K,
+                          "how": f"compress(batch k) on its own host thread(s) / context(s) while earlier batches are decompressed on "
+                                 f"another ({stream_how}); {K} batches timed including fill and drain; every batch makes the whole round trip"}
+        if rank == 0 and stream_rec and os.environ.get("LZ4B200_DEBUG"):
             print(f"# e2e stream of {K} batches: {1e3 * stream_s:.2f} ms per batch (serial {1e3 * e2e_serial_s:.2f} ms)", file=sys.stderr)
     del h_comp2
     per_rank = None
@@ -757,7 +771,7 @@ def run_ours(args):
                 "one_step_at_a_time": {"value": world * mib_rank / e2e_s, "ms_per_step": 1e3 * e2e_s},
                 "serial_ms_per_step": 1e3 * e2e_serial_s, "chunks": best_chunks, "per_rank": per_rank,
                 "compress_call_ms": 1e3 * float(np.mean([c for c, _ in call_t])),
-                "decompress_call_ms": 1e3 * float(np.mean([d for _, d in call_t])), "link": link, "stream": stream_rec,
+                "decompress_call_ms": 1e3 * float(np.mean([d for _, d in call_t])), "link": link, "stream": stream_rec if stream_rec else ({"error": stream_failed} if stream_failed else None),
                 "api": "lz4b200_compress_batch_host + lz4b200_decompress_batch_host (pinned host buffers); "
                        + (stream_rec["how"] if (stream_rec and stream_s < e2e_s) else e2e_how)},
         "gpu_launches": 2 * args.steps,
